@@ -1,0 +1,181 @@
+"""Synthetic LJ-liquid-like trajectories in the LAMMPS text-dump format the reference reads.
+
+The reference reader (reference snapshot.c:166-382) accepts exactly this layout::
+
+    ITEM: TIMESTEP
+    <step>
+    ITEM: NUMBER OF ATOMS
+    <N>
+    ITEM: BOX BOUNDS pp pp pp
+    <xlo> <xhi>
+    <ylo> <yhi>
+    <zlo> <zhi>
+    ITEM: ATOMS id type xu yu zu
+    <id> <type> <xu> <yu> <zu>          (N lines, single-space separated, snapshot.c:22)
+
+Atoms are identified by *line order* (``id`` is parsed and ignored, snapshot.c:357-368), so
+every frame lists the atoms in the same order.
+
+Workload shape: fcc lattice ``N = 4 n^3`` at reduced density 0.8442 in a
+cubic box ``L = (N / 0.8442)^(1/3)``, Gaussian thermal jitter ``sigma0`` per axis, then an
+*unwrapped* Gaussian random walk with ``sigma_step`` per axis per frame.
+"""
+from __future__ import annotations
+
+import io
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+RHO_STAR = 0.8442
+SIGMA0 = 0.10
+SIGMA_STEP = 0.077
+DEFAULT_SEED = 20261019
+
+
+@dataclass
+class Trajectory:
+    """positions[f, n, 3] (float64, unwrapped), box bounds per frame [f, 3, 2], timesteps[f]."""
+
+    positions: np.ndarray
+    box: np.ndarray
+    timesteps: np.ndarray
+    types: np.ndarray
+
+    @property
+    def n_frames(self) -> int:
+        return self.positions.shape[0]
+
+    @property
+    def n_atoms(self) -> int:
+        return self.positions.shape[1]
+
+
+def fcc_lattice(n_cells: int, box_len: float) -> np.ndarray:
+    """4 n^3 fcc sites in [0, L)^3, ordered cell-major then basis."""
+    a = box_len / n_cells
+    basis = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.5]])
+    idx = np.arange(n_cells)
+    cells = np.stack(np.meshgrid(idx, idx, idx, indexing="ij"), axis=-1).reshape(-1, 3)
+    sites = (cells[:, None, :] + basis[None, :, :]).reshape(-1, 3)
+    return sites * a
+
+
+def box_length(n_atoms: int, rho: float = RHO_STAR) -> float:
+    return float((n_atoms / rho) ** (1.0 / 3.0))
+
+
+def make_trajectory(
+    n_cells: int = 2,
+    n_frames: int = 40,
+    seed: int = DEFAULT_SEED,
+    sigma0: float = SIGMA0,
+    sigma_step: float = SIGMA_STEP,
+    n_atoms: int | None = None,
+    drift: tuple[float, float, float] = (0.0, 0.0, 0.0),
+    box_jitter: float = 0.0,
+    round_decimals: int | None = 6,
+) -> Trajectory:
+    """Random-walk liquid.  ``n_atoms`` (optional) truncates the lattice to a ragged count.
+
+    ``box_jitter`` > 0 makes the box length fluctuate per frame (NPT-like) to exercise the
+    reference's per-frame ``kVal = 2 pi / L`` (lmp2sqt.c:1620,1632).  ``round_decimals`` rounds
+    the coordinates to what the text dump will carry (``%.6f``) so that array and file agree.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_full = 4 * n_cells**3
+    L = box_length(n_full)
+    base = fcc_lattice(n_cells, L)
+    if n_atoms is not None:
+        base = base[:n_atoms]
+    n = base.shape[0]
+    pos0 = base + rng.normal(0.0, sigma0, size=(n, 3))
+    steps = rng.normal(0.0, sigma_step, size=(n_frames, n, 3))
+    steps[0] = 0.0
+    steps += np.asarray(drift)[None, None, :] * (np.arange(n_frames) > 0)[:, None, None]
+    pos = pos0[None] + np.cumsum(steps, axis=0)
+    box = np.zeros((n_frames, 3, 2))
+    if box_jitter > 0:
+        Ls = L * (1.0 + box_jitter * rng.standard_normal(n_frames))
+    else:
+        Ls = np.full(n_frames, L)
+    box[:, :, 1] = Ls[:, None]
+    if round_decimals is not None:
+        pos = np.round(pos, round_decimals)
+        box = np.round(box, round_decimals)
+    return Trajectory(pos, box, np.arange(n_frames, dtype=np.int64) * 100, np.ones(n, dtype=np.int32))
+
+
+def static_trajectory(n_cells: int, n_frames: int, seed: int = DEFAULT_SEED) -> Trajectory:
+    """All frames identical: F_s = 1, F(q,t) = S(q), MSD = 0 (SURVEY.md section 4 KAT)."""
+    t = make_trajectory(n_cells, 1, seed)
+    return Trajectory(
+        np.repeat(t.positions, n_frames, axis=0),
+        np.repeat(t.box, n_frames, axis=0),
+        np.arange(n_frames, dtype=np.int64) * 100,
+        t.types,
+    )
+
+
+def translating_trajectory(n_atoms: int, n_frames: int, d=(0.1, 0.0, 0.0), box_len: float = 10.0,
+                           seed: int = DEFAULT_SEED) -> Trajectory:
+    """Rigid translation by ``d`` per frame: F_s(q_m, tau) = 1/3 sum_a cos(m k0 d_a tau)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p0 = np.round(rng.uniform(0.0, box_len, size=(n_atoms, 3)), 6)
+    pos = p0[None] + np.arange(n_frames)[:, None, None] * np.asarray(d)[None, None, :]
+    box = np.zeros((n_frames, 3, 2))
+    box[:, :, 1] = box_len
+    return Trajectory(np.round(pos, 6), box, np.arange(n_frames, dtype=np.int64),
+                      np.ones(n_atoms, dtype=np.int32))
+
+
+def cubic_lattice_trajectory(n_side: int, n_frames: int, a: float = 1.0) -> Trajectory:
+    """Simple-cubic lattice, static: S(q_m) = N if n_side | m else 0."""
+    idx = np.arange(n_side)
+    p0 = np.stack(np.meshgrid(idx, idx, idx, indexing="ij"), axis=-1).reshape(-1, 3) * a
+    pos = np.repeat(p0[None].astype(np.float64), n_frames, axis=0)
+    box = np.zeros((n_frames, 3, 2))
+    box[:, :, 1] = n_side * a
+    return Trajectory(pos, box, np.arange(n_frames, dtype=np.int64), np.ones(len(p0), dtype=np.int32))
+
+
+def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None) -> None:
+    """Write ``traj`` as a LAMMPS text dump (``%.6f`` coordinates, ids 1..N in fixed order)."""
+    own = isinstance(path_or_file, (str, os.PathLike))
+    f = open(path_or_file, "w") if own else path_or_file
+    try:
+        n = traj.n_atoms
+        ids = np.arange(1, n + 1)
+        rng = range(traj.n_frames)[frames] if frames is not None else range(traj.n_frames)
+        for fi in rng:
+            b = traj.box[fi]
+            f.write("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % (traj.timesteps[fi], n))
+            for a in range(3):
+                f.write("%.6f %.6f\n" % (b[a, 0], b[a, 1]))
+            f.write("ITEM: ATOMS id type xu yu zu\n")
+            buf = io.StringIO()
+            p = traj.positions[fi]
+            np.savetxt(buf, np.column_stack([ids, traj.types, p]), fmt="%d %d %.6f %.6f %.6f")
+            f.write(buf.getvalue())
+    finally:
+        if own:
+            f.close()
+
+
+def write_deck(path, kVal=0.0981748, deltaT=0.06, mass=1.0, rVal=0.2, limitCorrAv=0,
+               nCBuffer=5, nCSpatial=4, nCTime=10, nCSkip=None) -> None:
+    """Write an ``in.lmp2sqt`` deck in the reference's NameList syntax (lmp2sqt.c:2126-2169)."""
+    with open(path, "w") as f:
+        f.write("NameList -- data\n")
+        f.write("kVal\t\t%#g \n" % kVal)
+        f.write("deltaT\t\t%#g \n" % deltaT)
+        f.write("mass\t\t%#g \n" % mass)
+        f.write("rVal\t\t%#g \n" % rVal)
+        f.write("limitCorrAv\t%d \n" % limitCorrAv)
+        f.write("nCBuffer\t%d \n" % nCBuffer)
+        f.write("nCSpatial\t%d \n" % nCSpatial)
+        f.write("nCTime\t\t%d \n" % nCTime)
+        if nCSkip is not None:
+            f.write("nCSkip\t\t%d \n" % nCSkip)
+        f.write("----\n")

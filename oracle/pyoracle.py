@@ -1,0 +1,399 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to the two CPU checkers under ``oracle/``.
+
+* :class:`OraclePort`  -- ``oracle/libsqt_oracle.so``, our plain-C restatement (sqt_oracle.c).
+* :class:`ReferenceLib` -- ``oracle/_ref/liblmp2sqt_ref.so``, the UNMODIFIED reference compiled
+  as a shared library by ``oracle/Makefile`` (``main`` renamed on the command line), driven
+  in-process exactly the way the reference's ``main`` drives it (lmp2sqt.c:117-336) so the raw
+  fp64 globals can be read before ``prePrintProcess`` rounds them into ``%8.4g`` text.
+  The reference keeps all state in file-scope globals, so use one *process* per run:
+  :func:`run_reference` does that for you.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline / ``--impl reference``
+legs may import this module.  The product package ``lmp2sqt_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libsqt_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "liblmp2sqt_ref.so")
+REF_BIN = os.path.join(HERE, "_ref", "lmp2sqt_ref.out")
+REF_ANALYSIS_BIN = os.path.join(HERE, "_ref", "analysis_binary_ref.out")
+
+NAMES2D = ["avF", "StdDevF", "avF_s", "StdDevF_s", "avF_d", "StdDevF_d", "avDrTable"]
+NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv"]
+
+
+def build(force: bool = False) -> None:
+    """Compile the restatement (always possible) and, where /root/reference exists, the reference."""
+    if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(HERE, "sqt_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    if os.path.exists("/root/reference/lmp2sqt.c") and (force or not os.path.exists(REF_SO)):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_SO) and os.path.exists(REF_BIN)
+
+
+class _Params(C.Structure):
+    _fields_ = [("kVal", C.c_double), ("deltaT", C.c_double), ("mass", C.c_double), ("rVal", C.c_double),
+                ("limitCorrAv", C.c_int), ("nCBuffer", C.c_int), ("nCSpatial", C.c_int), ("nCTime", C.c_int),
+                ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int)]
+
+
+class OraclePort:
+    """The plain-C restatement.  Method names follow the reference's call seam."""
+
+    def __init__(self, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=0, deltaT=0.06,
+                 kVal=0.0981748, mass=1.0, flag_f=True, flag_F=True, flag_t=True):
+        build()
+        L = C.CDLL(PORT_SO)
+        L.sqt_oracle_create.restype = C.c_void_p
+        L.sqt_oracle_create.argtypes = [C.POINTER(_Params)]
+        for fn in ("sqt_oracle_destroy", "sqt_oracle_begin_file"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+            getattr(L, fn).restype = None
+        L.sqt_oracle_push_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.sqt_oracle_finish.argtypes = [C.c_void_p]
+        L.sqt_oracle_set_limit.argtypes = [C.c_void_p, C.c_int]
+        L.sqt_oracle_set_limit.restype = None
+        for fn in ("countCorrAv", "printed_count", "number_call_print", "limitCorrAv", "nPtls"):
+            f = getattr(L, "sqt_oracle_" + fn)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_int
+        L.sqt_oracle_buffer_count.argtypes = [C.c_void_p, C.c_int]
+        L.sqt_oracle_kVal.argtypes = [C.c_void_p]
+        L.sqt_oracle_kVal.restype = C.c_double
+        for fn in ("raw2d", "printed2d", "raw1d", "printed1d"):
+            f = getattr(L, "sqt_oracle_" + fn)
+            f.argtypes = [C.c_void_p, C.c_int]
+            f.restype = C.POINTER(C.c_double)
+        for fn in ("factorDr", "rho"):
+            f = getattr(L, "sqt_oracle_" + fn)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.POINTER(C.c_double)
+        self.L = L
+        self.S, self.T = nCSpatial, nCTime
+        self.B = max(1, min(nCBuffer, nCTime))
+        p = _Params(kVal, deltaT, mass, rVal, limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip,
+                    int(flag_f), int(flag_F), int(flag_t))
+        self.h = L.sqt_oracle_create(C.byref(p))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.sqt_oracle_destroy(self.h)
+            self.h = None
+
+    def begin_file(self):
+        self.L.sqt_oracle_begin_file(self.h)
+
+    def push_frame(self, xyz: np.ndarray, xlo: float, xhi: float) -> int:
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        rc = self.L.sqt_oracle_push_frame(self.h, xyz.ctypes.data, xyz.shape[0], float(xlo), float(xhi))
+        if rc < 0:
+            raise RuntimeError("oracle push_frame failed rc=%d" % rc)
+        return rc
+
+    def finish(self) -> int:
+        return self.L.sqt_oracle_finish(self.h)
+
+    def set_limit(self, v):
+        self.L.sqt_oracle_set_limit(self.h, int(v))
+
+    @property
+    def countCorrAv(self):
+        return self.L.sqt_oracle_countCorrAv(self.h)
+
+    @property
+    def printed_count(self):
+        return self.L.sqt_oracle_printed_count(self.h)
+
+    @property
+    def kVal(self):
+        return self.L.sqt_oracle_kVal(self.h)
+
+    def buffer_counts(self):
+        return [self.L.sqt_oracle_buffer_count(self.h, nb) for nb in range(self.B)]
+
+    def _arr(self, fn, which, shape):
+        p = getattr(self.L, "sqt_oracle_" + fn)(self.h, which)
+        return np.ctypeslib.as_array(p, shape=shape).copy()
+
+    def raw(self) -> dict:
+        d = {n: self._arr("raw2d", i, (self.S, self.T)) for i, n in enumerate(NAMES2D)}
+        d.update({n: self._arr("raw1d", i, (self.T,)) for i, n in enumerate(NAMES1D)})
+        d["countCorrAv"] = self.countCorrAv
+        return d
+
+    def printed(self) -> dict:
+        d = {n: self._arr("printed2d", i, (self.S, self.T)) for i, n in enumerate(NAMES2D)}
+        d.update({n: self._arr("printed1d", i, (self.T,)) for i, n in enumerate(NAMES1D)})
+        d["countCorrAv"] = self.printed_count
+        d["kVal"] = self.kVal
+        return d
+
+    def rho(self):
+        return np.ctypeslib.as_array(self.L.sqt_oracle_rho(self.h), shape=(3, self.S, 2)).copy()
+
+    def factorDr(self):
+        return np.ctypeslib.as_array(self.L.sqt_oracle_factorDr(self.h), shape=(self.S,)).copy()
+
+
+def run_port(traj, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=0, flags="Ft",
+             files=None, finish=True):
+    """Drive the restatement over a trajectory (or a list of trajectories = several dump files)
+    the way the reference's ``main`` would, including its limitCorrAv bookkeeping
+    (lmp2sqt.c:221-247).  Returns (printed dict | None, raw dict, per-frame log)."""
+    trajs = files if files is not None else [traj]
+    flag_F = "F" in flags
+    flag_f = flag_F or "f" in flags
+    flag_t = "t" in flags
+    o = OraclePort(nCSpatial, nCTime, nCBuffer, nCSkip, rVal, 0, flag_f=flag_f, flag_F=flag_F, flag_t=flag_t)
+    limit = limitCorrAv
+    B = min(nCBuffer, nCTime)
+    use = []
+    for t in trajs:
+        n_snap = t.n_frames
+        if n_snap < 5 or int((n_snap - nCTime) / (nCTime // B)) < 1:  # C int division, lmp2sqt.c:228
+            use.append(False)
+            continue
+        limit += (n_snap - nCTime) // (nCTime // B)  # lmp2sqt.c:244
+        use.append(True)
+    o.set_limit(limit)
+    log = []
+    printed = None
+    for t, u in zip(trajs, use):
+        if not u:
+            continue
+        o.begin_file()
+        for f in range(t.n_frames):
+            rc = o.push_frame(t.positions[f], t.box[f, 0, 0], t.box[f, 0, 1])
+            log.append((o.countCorrAv, tuple(o.buffer_counts())))
+            if rc == 1:
+                printed = o.printed()
+    raw = o.raw()
+    if finish and o.finish():
+        printed = o.printed()
+    return printed, raw, log
+
+
+# ----------------------------------------------------------------------------------------------
+# The unmodified reference, in-process.
+# ----------------------------------------------------------------------------------------------
+ATOM_DTYPE = np.dtype([("id", "i4"), ("type", "i4"), ("x", "f8"), ("y", "f8"), ("z", "f8"),
+                       ("mux", "f8"), ("muy", "f8"), ("muz", "f8"), ("vx", "f8"), ("vy", "f8"),
+                       ("vz", "f8"), ("mu1", "f8"), ("atomType", "i4")], align=True)  # snapshot.h:95-110
+assert ATOM_DTYPE.itemsize == 96
+
+
+class _Box3(C.Structure):  # snapshot.h:118-126
+    _fields_ = [("xlow", C.c_double), ("xhigh", C.c_double), ("ylow", C.c_double), ("yhigh", C.c_double),
+                ("zlow", C.c_double), ("zhigh", C.c_double), ("pbcTYPE", C.c_int)]
+
+
+class _Snapshot(C.Structure):  # snapshot.h:132-138
+    _fields_ = [("timestep", C.c_long), ("NumAtoms", C.c_int), ("Box", _Box3), ("atoms", C.c_void_p),
+                ("snapFlag", C.c_int)]
+
+
+class _MakeSqtClass(C.Structure):  # lmp2sqt.h:156-162
+    _fields_ = [("tBuf", C.c_void_p), ("flag_alloc", C.c_int), ("flag_alloc_more", C.c_int),
+                ("snap", C.POINTER(_Snapshot)), ("nSkip", C.c_int)]
+
+
+class ReferenceLib:
+    """Drives the reference's own functions.  ONE instance per process (file-scope globals)."""
+
+    def __init__(self, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=0, deltaT=0.06,
+                 kVal=0.0981748, mass=1.0, flags="Ft"):
+        L = C.CDLL(REF_SO)
+        self.L = L
+        g = lambda name, t: t.in_dll(L, name)
+        self._g = g
+        g("kVal", C.c_double).value = kVal
+        g("deltaT", C.c_double).value = deltaT
+        g("mass", C.c_double).value = mass
+        g("rVal", C.c_double).value = rVal
+        g("nCSpatial", C.c_int).value = nCSpatial
+        g("nCTime", C.c_int).value = nCTime
+        g("nCBuffer", C.c_int).value = max(1, min(nCBuffer, nCTime))  # lmp2sqt.c:2105, 240-242
+        g("nCSkip", C.c_int).value = nCSkip
+        g("limitCorrAv", C.c_int).value = limitCorrAv
+        flag_F = "F" in flags
+        g("flag_F", C.c_bool).value = flag_F
+        g("flag_f", C.c_bool).value = flag_F or ("f" in flags)
+        g("flag_t", C.c_bool).value = "t" in flags
+        self.S, self.T, self.B = nCSpatial, nCTime, max(1, min(nCBuffer, nCTime))
+        self.cl = _MakeSqtClass()
+        C.c_void_p.in_dll(L, "classSqt").value = C.addressof(self.cl)
+        for fn in ("InitSpacetimeCorr", "EvalSpacetimeCorr", "PrintProcess"):
+            getattr(L, fn).argtypes = [C.POINTER(_MakeSqtClass)]
+            getattr(L, fn).restype = None
+        L.prePrintProcess.restype = None
+        self._keep = None
+
+    def set_limit(self, v):
+        self._g("limitCorrAv", C.c_int).value = int(v)
+
+    def begin_file(self):
+        self.L.InitSpacetimeCorr(C.byref(self.cl))
+
+    def push_frame(self, xyz: np.ndarray, xlo, xhi, box_yz=None) -> float:
+        """EvalSpacetimeCorr on a Snapshot built from ``xyz``; returns the call's wall seconds."""
+        n = xyz.shape[0]
+        atoms = np.zeros(n, dtype=ATOM_DTYPE)
+        atoms["id"] = np.arange(1, n + 1)
+        atoms["type"] = 1
+        atoms["x"], atoms["y"], atoms["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        snap = _Snapshot()
+        snap.timestep = 0
+        snap.NumAtoms = n
+        ylo, yhi, zlo, zhi = box_yz if box_yz is not None else (xlo, xhi, xlo, xhi)
+        snap.Box = _Box3(xlo, xhi, ylo, yhi, zlo, zhi, 7)
+        snap.atoms = atoms.ctypes.data
+        self._keep = (atoms, snap)
+        self.cl.snap = C.pointer(snap)
+        t0 = time.perf_counter()
+        self.L.EvalSpacetimeCorr(C.byref(self.cl))
+        return time.perf_counter() - t0
+
+    @property
+    def countCorrAv(self):
+        return self._g("countCorrAv", C.c_int).value
+
+    @property
+    def number_call_print(self):
+        return self._g("Number_call_Print", C.c_int).value
+
+    def _a2(self, name):
+        pp = C.POINTER(C.POINTER(C.c_double)).in_dll(self.L, name)
+        if not pp:
+            return np.zeros((self.S, self.T))
+        return np.ctypeslib.as_array(pp[0], shape=(self.S, self.T)).copy()  # AllocMem2: one contiguous block
+
+    def _a1(self, name):
+        p = C.POINTER(C.c_double).in_dll(self.L, name)
+        if not p:
+            return np.zeros(self.T)
+        return np.ctypeslib.as_array(p, shape=(self.T,)).copy()
+
+    def arrays(self) -> dict:
+        m = {"avF": "avF_qq2", "StdDevF": "StdDevF_qq2", "avF_s": "avF_s_qq2", "StdDevF_s": "StdDevF_s_qq2",
+             "avF_d": "avF_d_qq2", "StdDevF_d": "StdDevF_d_qq2", "avDrTable": "avDrTable"}
+        d = {k: self._a2(v) for k, v in m.items()}
+        for n in NAMES1D:
+            d[n] = self._a1(n)
+        d["countCorrAv"] = self.countCorrAv
+        d["kVal"] = self._g("kVal", C.c_double).value
+        return d
+
+    def pre_print(self):
+        """prePrintProcess (lmp2sqt.c:576-675): normalise the sums in place."""
+        self.L.prePrintProcess()
+
+
+def _ref_worker(job_path: str) -> None:
+    with open(job_path, "rb") as f:
+        job = pickle.load(f)
+    os.chdir(job["cwd"])
+    ref = ReferenceLib(**job["params"])
+    ref.set_limit(job["limit"])
+    times, log = [], []
+    for pos, box in job["files"]:
+        ref.begin_file()
+        for fi in range(pos.shape[0]):
+            dt = ref.push_frame(pos[fi], box[fi, 0, 0], box[fi, 0, 1])
+            times.append(dt)
+            log.append(ref.countCorrAv)
+    raw = ref.arrays()
+    out = {"raw": raw, "times": times, "log": log, "n_print": ref.number_call_print}
+    if job.get("normalise", True) and raw["countCorrAv"] > 0:
+        ref.pre_print()
+        out["printed"] = ref.arrays()
+        out["printed"]["countCorrAv"] = raw["countCorrAv"]
+    with open(job["out"], "wb") as f:
+        pickle.dump(out, f)
+
+
+def run_reference(trajs, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, flags="Ft", threads=1,
+                  limit=10**9, normalise=True) -> dict:
+    """Run the unmodified reference in a fresh process over ``trajs`` (list of Trajectory = input
+    files).  ``limit`` is the in-memory limitCorrAv (default: never flush mid-run, so that the raw
+    sums of the whole run can be read).  OMP_NUM_THREADS=``threads`` (1 for anything MSD-like: the
+    reference's loop at lmp2sqt.c:1377 races)."""
+    if not have_reference():
+        raise RuntimeError("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")
+    with tempfile.TemporaryDirectory() as td:
+        job = {"cwd": td, "out": os.path.join(td, "out.pkl"), "limit": int(limit), "normalise": normalise,
+               "params": dict(nCSpatial=nCSpatial, nCTime=nCTime, nCBuffer=nCBuffer, nCSkip=nCSkip, rVal=rVal, flags=flags),
+               "files": [(t.positions, t.box) for t in trajs]}
+        jp = os.path.join(td, "job.pkl")
+        with open(jp, "wb") as f:
+            pickle.dump(job, f)
+        # MALLOC_PERTURB_=255 makes glibc hand out zero-filled blocks: the reference never
+        # initialises TBuf.rrMSDCM (lmp2sqt.c:1325-1333 vs :1450); zero is what a fresh heap gives its CLI.
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), MALLOC_PERTURB_="255",
+                   GLIBC_TUNABLES="glibc.malloc.tcache_count=0")  # tcache hits skip the perturb fill
+        code = "import sys; sys.path.insert(0, %r); import pyoracle; pyoracle._ref_worker(%r)" % (HERE, jp)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference worker failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+        with open(job["out"], "rb") as f:
+            return pickle.load(f)
+
+
+def run_reference_cli(workdir, deck_name, dump_names, flags=("-F", "-t"), threads=1) -> subprocess.CompletedProcess:
+    """Run the unmodified reference *binary* in ``workdir`` (it writes its outputs and rewrites the deck there)."""
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    return subprocess.run([REF_BIN, *flags, "-i", deck_name, *dump_names], cwd=workdir, env=env,
+                          capture_output=True, text=True)
+
+
+def parse_output_binary(path, nCSpatial, nCTime) -> dict:
+    """Parse the reference's output.binary (layout: lmp2sqt.c:768-864).  Arrays come back [nCTime][nCSpatial]."""
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    off = 0
+
+    def take(fmt, n=1):
+        nonlocal off
+        a = np.frombuffer(data, dtype=fmt, count=n, offset=off)
+        off += a.nbytes
+        return a
+
+    hl = int(take("<i4")[0])
+    out["magic"] = data[off:off + hl].decode()
+    off += hl
+    ntypes = int(take("<i4")[0])
+    out["sets"] = []
+    while off < len(data):
+        for _ in range(ntypes):
+            ln = int(take("<i4")[0])
+            name = data[off:off + ln].decode()
+            off += ln
+            kVal, dt, rVal = take("<f8", 3)
+            yes = int(take("<i4")[0])
+            arr = take("<f8", nCSpatial * nCTime).reshape(nCTime, nCSpatial).copy() if yes else None
+            out[name] = arr
+            out["kVal"], out["deltaT"], out["rVal"] = float(kVal), float(dt), float(rVal)
+        break
+    out["size"] = len(data)
+    out["consumed"] = off
+    return out
+
+
+if __name__ == "__main__":
+    build(force=True)
+    print(json.dumps({"port": os.path.exists(PORT_SO), "reference": have_reference()}))

@@ -1,0 +1,74 @@
+/*
+ * sqt_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C CPU restatement of the lmp2sqt space-time-correlation hot path
+ * (reference lmp2sqt.c:1599-1650 EvalSpacetimeCorr and its callees), used as the
+ * parity checker for the CUDA path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg may load this library; the product path never does.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this restatement
+ * against the unmodified reference (oracle/_ref/liblmp2sqt_ref.so built from
+ * /root/reference by oracle/Makefile) and against the committed golden files in
+ * tests/golden/ that the reference binary itself produced.
+ */
+#ifndef SQT_ORACLE_H
+#define SQT_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqt_oracle sqt_oracle;
+
+/* Mirrors the deck (lmp2sqt.c:82-92) and the getopt flags (lmp2sqt.c:152-191). */
+typedef struct {
+	double kVal, deltaT, mass, rVal;
+	int limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip;
+	int flag_f, flag_F, flag_t;
+} sqt_oracle_params;
+
+sqt_oracle *sqt_oracle_create(const sqt_oracle_params *p);
+void sqt_oracle_destroy(sqt_oracle *o);
+
+/* InitSpacetimeCorr (lmp2sqt.c:446-475): ring phase reset, once per input file. */
+void sqt_oracle_begin_file(sqt_oracle *o);
+
+/* EvalSpacetimeCorr (lmp2sqt.c:1599-1650) on one frame.  xyz is AoS [n][3].
+ * Returns 1 when AccumSpacetimeCorr hit countCorrAv == limitCorrAv in this frame
+ * (the reference calls PrintProcess there, lmp2sqt.c:438-440): the normalised
+ * results were stored in the "printed" arrays and the averages were zeroed;
+ * 0 otherwise; <0 on error. */
+int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, double xhi);
+
+/* End-of-run print (lmp2sqt.c:327-333): only if nothing was printed before,
+ * limitCorrAv = countCorrAv, then PrintProcess.  Returns 1 if it printed now. */
+int sqt_oracle_finish(sqt_oracle *o);
+
+void sqt_oracle_set_limit(sqt_oracle *o, int limitCorrAv);
+
+/* Scalars. */
+int sqt_oracle_countCorrAv(const sqt_oracle *o);       /* live counter (reset by a print) */
+int sqt_oracle_printed_count(const sqt_oracle *o);     /* countCorrAv at the last print */
+int sqt_oracle_number_call_print(const sqt_oracle *o);
+int sqt_oracle_limitCorrAv(const sqt_oracle *o);
+double sqt_oracle_kVal(const sqt_oracle *o);           /* last 2*pi/L (lmp2sqt.c:1632) */
+int sqt_oracle_nPtls(const sqt_oracle *o);
+int sqt_oracle_buffer_count(const sqt_oracle *o, int nb);
+
+/* Arrays.  "raw" = running sums before normalisation; "printed" = what
+ * prePrintProcess (lmp2sqt.c:576-675) left in the arrays at the last print.
+ * 2-D arrays are [nCSpatial][nCTime] row-major (the reference's avF_qq2[nk][nt]).
+ * which: 0 avF, 1 StdDevF, 2 avF_s, 3 StdDevF_s, 4 avF_d, 5 StdDevF_d, 6 avDrTable */
+const double *sqt_oracle_raw2d(const sqt_oracle *o, int which);
+const double *sqt_oracle_printed2d(const sqt_oracle *o, int which);
+/* which: 0 rrMSDAv, 1 rrMQDAv, 2 rrMSDCMAv  (length nCTime) */
+const double *sqt_oracle_raw1d(const sqt_oracle *o, int which);
+const double *sqt_oracle_printed1d(const sqt_oracle *o, int which);
+const double *sqt_oracle_factorDr(const sqt_oracle *o);   /* lmp2sqt.c:1987-2009 */
+/* current-frame rho(k): [3][nCSpatial][2]  (lmp2sqt.c:1173-1174 marker layout) */
+const double *sqt_oracle_rho(const sqt_oracle *o);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

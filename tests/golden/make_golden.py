@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/* by running the UNMODIFIED reference here (needs /root/reference
+built into oracle/_ref by `make -C oracle ref`).  The outputs are committed so that the CPU and
+GPU test-suites can check the oracle restatement, the host writers and the CUDA path without the
+reference being present (it does not exist on the GPU box).
+
+Per case <name>/ :
+  dump*.lammpstrj.gz   input text dump(s)                      (synthetic, lmp2sqt_b200.synth)
+  in.lmp2sqt           deck as given to the reference
+  in.lmp2sqt.after     deck as the reference rewrote it        (lmp2sqt.c:2112-2125)
+  output.binary / output.txt / SSF000.info / Dt000.info / output.log / stdout.txt
+                       what `lmp2sqt_ref.out <flags> -i in.lmp2sqt dump...` wrote (OMP_NUM_THREADS=1)
+  arrays.npz           raw fp64 sums + normalised arrays read from the reference's globals when the
+                       same frames are pushed through its own EvalSpacetimeCorr in-process
+                       (oracle/pyoracle.py:ReferenceLib), with limitCorrAv large (no mid-run flush)
+  case.json            parameters
+"""
+import glob
+import gzip
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pyoracle  # noqa: E402
+from lmp2sqt_b200 import synth  # noqa: E402
+
+CASES = {
+    # mid-run print: deck limitCorrAv 0 + computed 15 is reached at frame 38
+    "g1_midrun_print": dict(traj=[dict(n_cells=2, n_frames=40, seed=1)], S=4, T=10, B=5, skip=None, limit=0, flags="Ft"),
+    # shipped-deck style: huge limitCorrAv, end-of-run print covers all buffers
+    "g2_final_print": dict(traj=[dict(n_cells=2, n_frames=40, seed=2)], S=4, T=10, B=5, skip=None, limit=14825, flags="Ft"),
+    # ragged N, B == T, nCSkip 1, fluctuating box, two input files
+    "g3_two_files_skip": dict(traj=[dict(n_cells=3, n_atoms=50, n_frames=37, seed=3, box_jitter=0.01),
+                                    dict(n_cells=3, n_atoms=50, n_frames=29, seed=4, box_jitter=0.01)],
+                              S=6, T=8, B=8, skip=1, limit=14825, flags="Ft"),
+    # collective only (-f -t): self/cross blocks absent from output.binary
+    "g4_collective_only": dict(traj=[dict(n_cells=2, n_frames=33, seed=5)], S=5, T=6, B=3, skip=None, limit=14825, flags="ft"),
+    # in.lmp2sqt.150.smallQ-like ring (T = B = 150 is too slow for a fixture; 30/30 keeps the shape)
+    "g5_ring30": dict(traj=[dict(n_cells=3, n_frames=100, seed=6)], S=10, T=30, B=30, skip=None, limit=14825, flags="Ft"),
+}
+
+
+def main():
+    pyoracle.build()
+    assert pyoracle.have_reference(), "needs /root/reference"
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, c in CASES.items():
+        out = os.path.join(here, name)
+        shutil.rmtree(out, ignore_errors=True)
+        os.makedirs(out)
+        trajs = [synth.make_trajectory(**kw) for kw in c["traj"]]
+        with tempfile.TemporaryDirectory() as td:
+            dumps = []
+            for i, t in enumerate(trajs):
+                dn = "dump%d.lammpstrj" % i
+                synth.write_text_dump(t, os.path.join(td, dn))
+                dumps.append(dn)
+            synth.write_deck(os.path.join(td, "in.lmp2sqt"), limitCorrAv=c["limit"], nCBuffer=c["B"],
+                             nCSpatial=c["S"], nCTime=c["T"], nCSkip=c["skip"])
+            shutil.copy(os.path.join(td, "in.lmp2sqt"), os.path.join(out, "in.lmp2sqt"))
+            cli_flags = {"Ft": ("-F", "-t"), "ft": ("-f", "-t"), "F": ("-F",), "t": ("-t",)}[c["flags"]]
+            r = pyoracle.run_reference_cli(td, "in.lmp2sqt", dumps, flags=cli_flags, threads=1)
+            assert r.returncode == 0, r.stderr
+            with open(os.path.join(out, "stdout.txt"), "w") as f:
+                f.write(r.stdout)
+            shutil.copy(os.path.join(td, "in.lmp2sqt"), os.path.join(out, "in.lmp2sqt.after"))
+            for fn in ("output.binary", "output.txt", "output.log"):
+                if os.path.exists(os.path.join(td, fn)):
+                    shutil.copy(os.path.join(td, fn), os.path.join(out, fn))
+            for pat, dst in (("SSF000.info.*", "SSF000.info"), ("Dt000.info.*", "Dt000.info")):
+                g = glob.glob(os.path.join(td, pat))
+                if g:
+                    shutil.copy(g[0], os.path.join(out, dst))
+            for dn in dumps:
+                with open(os.path.join(td, dn), "rb") as fi, gzip.GzipFile(os.path.join(out, dn + ".gz"), "wb", mtime=0) as fo:
+                    fo.write(fi.read())
+        ref = pyoracle.run_reference(trajs, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0, flags=c["flags"], limit=10**9)
+        arrs = {"raw_" + k: v for k, v in ref["raw"].items()}
+        arrs.update({"printed_" + k: v for k, v in ref.get("printed", {}).items()})
+        arrs["count_log"] = np.asarray(ref["log"])
+        np.savez_compressed(os.path.join(out, "arrays.npz"), **arrs)
+        with open(os.path.join(out, "case.json"), "w") as f:
+            json.dump(c, f, indent=1)
+        print(name, "countCorrAv", ref["raw"]["countCorrAv"], sorted(os.listdir(out)))
+
+
+if __name__ == "__main__":
+    main()
