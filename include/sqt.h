@@ -1,0 +1,170 @@
+/*
+ * sqt.h -- C-ABI of the B200 space-time-correlation engine (libsqt_b200.so).
+ *
+ * Drop-in boundary for the hot path of infinitekh/lmp2sqt.  The reference has no plugin or
+ * FFI interface: it is one translation unit whose `main` makes four calls into the hot path
+ * (SURVEY.md section 8b).  Each entry point below replaces one of them; plain pointers and
+ * sizes only, no CUDA or torch types.
+ *
+ *   reference call (file:line)                              replaced by
+ *   ------------------------------------------------------  ---------------------------------
+ *   AllocArray / Alloc_more      lmp2sqt.c:1821, :1926       sqt_create (+ first sqt_push_frame)
+ *   limitCorrAv += floor(...)    lmp2sqt.c:244               sqt_set_limit
+ *   InitSpacetimeCorr(cl)        lmp2sqt.c:446, main :282    sqt_begin_file
+ *   cl->snap = ReadDump(fp)      lmp2sqt.c:295-298           sqt_stage_acquire (caller fills SoA)
+ *   EvalSpacetimeCorr(cl)        lmp2sqt.c:1599, main :300   sqt_push_frame / sqt_push_frame_device
+ *   PrintProcess(cl) mid-run     lmp2sqt.c:438-440           sqt_push_frame returns SQT_FLUSH,
+ *                                                            then sqt_fetch_results
+ *   PrintProcess(cl) end of run  lmp2sqt.c:327-333           sqt_finish
+ *
+ * Everything numerical between those calls (EvalOneTimeKspace :1144, SetWaitedTimeCorr :1260,
+ * EvalTwoTimeEach :1368, EvalTwoTimeKSpace :1477, AccumSpacetimeCorr :368) runs in hand-written
+ * sm_100a kernels on device-resident state.  Normalisation (prePrintProcess :576) and the file
+ * writers stay on the host (include/sqt_host.h) and consume `sqt_results`.
+ *
+ * Threading: one caller thread per handle (the reference is single threaded).  Calls are
+ * asynchronous with respect to the GPU; sqt_fetch_results / sqt_finish / sqt_sync synchronise.
+ * Errors: every function returns SQT_OK (0) or a positive status on success and a negative
+ * code on failure; sqt_last_error() gives the message.  There is NO CPU fallback: without a
+ * usable CUDA device sqt_create fails with SQT_ERR_CUDA.
+ */
+#ifndef SQT_H
+#define SQT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQT_OK 0
+#define SQT_FLUSH 1          /* countCorrAv reached limitCorrAv in this frame (lmp2sqt.c:438) */
+#define SQT_ERR_ARG (-1)
+#define SQT_ERR_CUDA (-2)
+#define SQT_ERR_NCCL (-3)
+#define SQT_ERR_STATE (-4)
+#define SQT_ERR_NOMEM (-5)
+
+typedef struct sqt_handle sqt_handle;
+
+/* The deck (lmp2sqt.c:82-92 DATALIST) and the getopt flags (lmp2sqt.c:152-191). */
+typedef struct {
+	double kVal, deltaT, mass, rVal;
+	int limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip;
+	int flag_f, flag_F, flag_t;
+	int device;          /* CUDA device ordinal this handle owns */
+	int reserved[7];     /* must be zero */
+} sqt_params;
+
+/*
+ * Raw running sums, exactly the arrays prePrintProcess (lmp2sqt.c:576-675) consumes, before
+ * normalisation.  2-D arrays are [nCSpatial][nCTime] row-major like the reference's
+ * avF_qq2[nk][nt].  The caller owns the arrays (sqt_results_alloc / sqt_results_free).
+ */
+typedef struct {
+	int nCSpatial, nCTime;
+	int countCorrAv;         /* completed buffers accumulated into the sums            */
+	int limitCorrAv;         /* value in force when the sums were latched              */
+	long long nPtls;         /* atoms per frame (all shards)                            */
+	double g_Vol;            /* L^3 of the last processed frame  (lmp2sqt.c:1621)       */
+	double kVal;             /* 2 pi / L of the last processed frame (lmp2sqt.c:1632)   */
+	double first_Vol;        /* L^3 of the FIRST processed frame (factorDr, :1991-2004) */
+	int first_limitCorrAv;   /* limitCorrAv at the first processed frame (:2004)        */
+	int number_call_print;   /* Number_call_Print after this print (lmp2sqt.c:674)      */
+	double *avF_qq2, *StdDevF_qq2, *avF_s_qq2, *StdDevF_s_qq2, *avF_d_qq2, *StdDevF_d_qq2;
+	double *avDrTable;
+	double *rrMSDAv, *rrMQDAv, *rrMSDCMAv;   /* [nCTime] */
+} sqt_results;
+
+int  sqt_results_alloc(sqt_results *r, int nCSpatial, int nCTime);
+void sqt_results_free(sqt_results *r);
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+int  sqt_create(const sqt_params *p, sqt_handle **out);
+void sqt_destroy(sqt_handle *h);
+const char *sqt_last_error(const sqt_handle *h);   /* h may be NULL: error of the last failed sqt_create */
+
+/* main's `limitCorrAv += floor((n_snap - nCTime)/(nCTime/nCBuffer))` (lmp2sqt.c:244) happens
+ * between GetNameList and the first frame; the host tells the engine the final value here. */
+int  sqt_set_limit(sqt_handle *h, int limitCorrAv);
+
+/* InitSpacetimeCorr (lmp2sqt.c:446-475): count[nb] = -nb*nCTime/nCBuffer, nSkip = 0.  Once per
+ * input file; the averages persist across files, partially filled buffers are discarded. */
+int  sqt_begin_file(sqt_handle *h);
+
+/* ---- frames ------------------------------------------------------------------------------ */
+/* Pinned host staging for the next frame, SoA: x[0..n), y[0..n), z[0..n) as doubles
+ * (3*n_atoms_local contiguous).  Double buffered: the pointer stays valid until the second
+ * following sqt_stage_acquire.  Blocks only if the slot's previous H2D copy is still in flight. */
+double *sqt_stage_acquire(sqt_handle *h, int n_atoms_local);
+
+/* EvalSpacetimeCorr (lmp2sqt.c:1599-1650) for one frame.  `soa` is either a buffer from
+ * sqt_stage_acquire (async H2D, no extra copy) or any host memory (copied synchronously into
+ * staging first).  n_atoms_local = atoms this handle owns (its particle shard, dump order);
+ * n_atoms_total = atoms in the frame over all shards.  xlo/xhi = x box bounds (L, kVal and
+ * g_Vol derive from x only, lmp2sqt.c:1620-1632).
+ * Returns SQT_OK, SQT_FLUSH, or <0. */
+int  sqt_push_frame(sqt_handle *h, const double *soa, int n_atoms_local, long long n_atoms_total,
+                    double xlo, double xhi);
+/* Same, for a frame already resident in device memory (SoA, 3*n_atoms_local doubles) on
+ * the handle's device -- the binary / on-device frame source path. */
+int  sqt_push_frame_device(sqt_handle *h, const double *d_soa, int n_atoms_local,
+                           long long n_atoms_total, double xlo, double xhi);
+
+/* ---- results ----------------------------------------------------------------------------- */
+/* After SQT_FLUSH: the sums latched at the flush (the averages were zeroed on the device
+ * exactly like ZeroAvSpacetimeCorr, lmp2sqt.c:366).  Otherwise: the current running sums.
+ * Synchronises.  On several shards every rank receives identical, fully reduced arrays. */
+int  sqt_fetch_results(sqt_handle *h, sqt_results *out);
+/* End of run (lmp2sqt.c:327-333): if nothing was printed yet, limitCorrAv = countCorrAv and the
+ * sums are returned (returns 1 = "print now"); returns 0 if a mid-run print already happened. */
+int  sqt_finish(sqt_handle *h, sqt_results *out);
+int  sqt_sync(sqt_handle *h);
+
+/* ---- introspection (bookkeeping parity tests, bench) ------------------------------------- */
+int  sqt_count_corr_av(const sqt_handle *h);
+int  sqt_buffer_count(const sqt_handle *h, int nb);       /* TBuf.count, lmp2sqt.h:69 */
+int  sqt_number_call_print(const sqt_handle *h);
+/* rho(k) of the last processed frame, [3][nCSpatial][2] (marker layout lmp2sqt.c:1173-1174). */
+int  sqt_get_rho(sqt_handle *h, double *out);
+long long sqt_kernel_launches(const sqt_handle *h);       /* launches of OUR kernels so far */
+/* CUDA-event timing of the dominant kernel (self_ring) on its own stream.  enable=1 starts
+ * recording (one event pair per launch); sqt_profile_read synchronises and returns the count
+ * and summed milliseconds since enable, then clears. */
+int  sqt_profile_enable(sqt_handle *h, int enable);
+int  sqt_profile_read(sqt_handle *h, long long *n_launches, double *ms_total);
+/* Device-side clock over a region of frames: start records an event on the engine's main
+ * stream; stop records one after the last pushed frame's collective stage, waits for it and
+ * returns the elapsed milliseconds (CUDA events, not host wall clock). */
+int  sqt_timer_start(sqt_handle *h);
+int  sqt_timer_stop(sqt_handle *h, double *ms);
+/* Human-readable description of the kernel configuration picked for this deck. */
+const char *sqt_kernel_config(const sqt_handle *h);
+
+/* ---- multi-GPU: one process (handle) per GPU, particle-sharded --------------------------- */
+/* Rank 0 obtains an opaque id (ncclUniqueId, 128 bytes) and ships it to the other ranks by
+ * whatever plumbing the host has (torch.distributed broadcast, MPI, a file...). */
+#define SQT_COMM_ID_BYTES 128
+int  sqt_comm_unique_id(void *id_out);
+int  sqt_comm_init(sqt_handle *h, const void *id, int rank, int nranks);
+
+/* ---- on-device synthetic frame source (bench workloads) ------------ */
+typedef struct sqt_synth sqt_synth;
+/* fcc lattice of 4*n_cells^3 sites at reduced density 0.8442, jitter 0.10, random walk
+ * 0.077/axis/frame, counter-based RNG keyed (seed, atom, frame): shard independent.
+ * The source owns atoms [first_atom, first_atom + n_atoms_local). */
+int  sqt_synth_create(int device, int n_cells, long long first_atom, int n_atoms_local,
+                      unsigned long long seed, sqt_synth **out);
+/* Advances to the next frame (frame 0 on the first call); returns the device SoA pointer. */
+const double *sqt_synth_next(sqt_synth *s);
+double sqt_synth_box_length(const sqt_synth *s);
+/* Copies the current frame into host memory (SoA, 3*n doubles). */
+int  sqt_synth_copy_to_host(sqt_synth *s, double *dst);
+void sqt_synth_destroy(sqt_synth *s);
+
+/* ---- roofline denominator: measured non-tensor FP64 FMA throughput ----------------------- */
+/* Runs a register-resident DFMA loop on every SM; returns TFLOP/s (FMA = 2 flops). */
+int  sqt_measure_dfma_peak(int device, double *tflops, double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+/*
+ * sqt_host.h -- host-side C code that stays on the CPU around the engine (libsqt_host.so):
+ * the deck, the LAMMPS text-dump reader, the normalisation and the result writers.  These keep
+ * the reference's file formats byte-for-byte so that the new path is a drop-in for
+ * `lmp2sqt.out -F -t -i deck dump...`.
+ *
+ *   reference (file:line)                                    here
+ *   -------------------------------------------------------  --------------------------------
+ *   GetNameList            lmp2sqt.c:2014-2111                sqt_deck_read
+ *   PrintNameList2File     lmp2sqt.c:2126-2169                sqt_deck_print
+ *   UpdateNameList         lmp2sqt.c:2112-2125                sqt_deck_write
+ *   ReadDumpForOnlyCheck   snapshot.c:25-165                  sqt_dump_read_header + sqt_dump_skip_atoms
+ *   ReadDump               snapshot.c:166-382                 sqt_dump_read_header + sqt_dump_read_atoms (SoA)
+ *   Alloc_more tail        lmp2sqt.c:1987-2009 (factorDr)     sqt_host_factor_dr
+ *   prePrintProcess        lmp2sqt.c:576-675                  sqt_host_normalise
+ *   PrintProcess           lmp2sqt.c:338-367                  sqt_host_print_process
+ *     PrintEtc             lmp2sqt.c:865-1093  (SSF, Dt)
+ *     PrintSpacetimeCorr   lmp2sqt.c:677-766   (output.txt)
+ *     PrintSpacetimeCorr_binary lmp2sqt.c:768-864 (output.binary)
+ */
+#ifndef SQT_HOST_H
+#define SQT_HOST_H
+
+#include <stdio.h>
+#include "sqt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQT_DECK_NNAMES 9
+typedef struct {
+	double kVal, deltaT, mass, rVal;
+	int limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip;
+	int status[SQT_DECK_NNAMES]; /* vStatus per name, DATALIST order: 0 no data, 1 ok, 2 missing, 3 extra, 4 multiply defined */
+} sqt_deck;
+
+/* Returns 1 if every name was read exactly once ("ok"), 0 otherwise (the reference ignores the
+ * value, lmp2sqt.c:199), -1 if the file does not exist (the reference then writes a template deck
+ * and exits; sqt_deck_write_template does the former). */
+int sqt_deck_read(const char *path, sqt_deck *d);
+int sqt_deck_print(FILE *fp, const sqt_deck *d);
+int sqt_deck_write(const char *path, const sqt_deck *d);
+int sqt_deck_write_template(const char *path);
+
+typedef struct {
+	long timestep;
+	int n_atoms;
+	double xlo, xhi, ylo, yhi, zlo, zhi;
+	int pbcType;
+	int style; /* 0: id type xu yu zu; 1: +vx vy vz; 2: +mux muy muz; 3: +mux muy muz vx vy vz */
+} sqt_frame_header;
+
+/* 1 = header read, 0 = end of file or not a frame (the reference stops the file there). */
+int sqt_dump_read_header(FILE *fp, sqt_frame_header *hd);
+/* Atom lines into SoA x[n], y[n], z[n] in file-line order (`id` is ignored, snapshot.c:357-368). 1 ok / 0 short file. */
+int sqt_dump_read_atoms(FILE *fp, const sqt_frame_header *hd, double *x, double *y, double *z);
+int sqt_dump_skip_atoms(FILE *fp, const sqt_frame_header *hd);
+
+/* factorDr[nr], lmp2sqt.c:1987-2009, from what the engine recorded at the first processed frame. */
+void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr);
+/* prePrintProcess: normalises r's arrays IN PLACE (like the reference does with its globals). */
+void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t);
+/* PrintProcess: normalise, then write SSF%03d.info.<date>, Dt%03d.info.<date>, output.txt,
+ * output.binary, output.log into `dir` (NULL = cwd).  `date` is the yymmdd suffix (NULL = today,
+ * lmp2sqt.c:127-132).  Returns 0 or -1. */
+int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t,
+                           const char *date);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,218 @@
+/*
+ * sqt_writers.c -- normalisation and result files, format-identical to the reference:
+ *   prePrintProcess            lmp2sqt.c:576-675
+ *   PrintProcess               lmp2sqt.c:338-367
+ *   PrintEtc (SSF, Dt)         lmp2sqt.c:865-1093
+ *   PrintSpacetimeCorr         lmp2sqt.c:677-766   output.txt
+ *   PrintSpacetimeCorr_binary  lmp2sqt.c:768-864   output.binary
+ * Input is the engine's raw sums (sqt_results); everything here is O(nCSpatial*nCTime) host work.
+ *
+ * Documented deviations (SURVEY.md section 7 "hard parts"):
+ *   - Dt columns msdx/msdy/msdz: the reference prints rrMSR1_R_Av, which is uninitialised memory
+ *     unless -s is given (lmp2sqt.c:427-431, 532-533); we print 0.
+ *   - 1/(N*N) uses a double product; the reference's int product overflows for N > 46340.
+ */
+#include "../../../include/sqt_host.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#define DIM 3
+
+static const char *k_txtCorr = "##space-time corr"; /* common.c:20 */
+static const char *k_header[4] = { "full-density", "self-density", "cross-density", "self-vanHove" };
+
+void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr)
+{
+	const double vol = r->first_Vol;
+	const double rho0 = (double)r->nPtls / vol;
+	double shell_Vol;
+	for (int nr = 0; nr < r->nCSpatial; nr++) {
+		if (nr == 0) shell_Vol = 4 * M_PI / 3. * pow(rVal, 3);
+		else shell_Vol = (4. / 3.) * M_PI * (pow((nr + 1) * rVal, 3) - pow(nr * rVal, 3));
+		factorDr[nr] = 1. / (pow(rho0, 2) * vol * shell_Vol * r->first_limitCorrAv);
+	}
+}
+
+void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t)
+{
+	const int S = r->nCSpatial, T = r->nCTime;
+	const double N = (double)r->nPtls;
+	const double inverseNptls = 1. / N;
+	const double inverseNptlsSq = 1. / (N * N);
+	const double average_number = 1. / (3.0 * r->countCorrAv);
+	if (flag_f) {
+		double *av[3] = { r->avF_qq2, r->avF_s_qq2, r->avF_d_qq2 };
+		double *sd[3] = { r->StdDevF_qq2, r->StdDevF_s_qq2, r->StdDevF_d_qq2 };
+		for (int q = 0; q < (flag_F ? 3 : 1); q++)
+			for (int e = 0; e < S * T; e++) {
+				double average = (av[q][e] * inverseNptls) * average_number;
+				double averageSq = (sd[q][e] * inverseNptlsSq) * average_number;
+				av[q][e] = average;
+				sd[q][e] = sqrt((averageSq - average * average));
+			}
+		double *factorDr = (double *)malloc(sizeof(double) * S);
+		sqt_host_factor_dr(r, d->rVal, factorDr);
+		for (int nt = 1; nt < T; nt++) /* lag 0 is left unscaled, lmp2sqt.c:626 */
+			for (int nr = 0; nr < S; nr++) r->avDrTable[nr * T + nt] *= factorDr[nr];
+		free(factorDr);
+	}
+	if (flag_t) {
+		const double scale_factor = 1. / (N * r->countCorrAv);
+		const double factor_msdcm = 1. / (r->countCorrAv);
+		for (int nt = 0; nt < T; nt++) {
+			r->rrMSDAv[nt] *= scale_factor;
+			r->rrMSDCMAv[nt] *= factor_msdcm;
+			r->rrMQDAv[nt] *= scale_factor;
+		}
+	}
+}
+
+static void join(char *out, size_t n, const char *dir, const char *name)
+{
+	if (dir && *dir) snprintf(out, n, "%s/%s", dir, name);
+	else snprintf(out, n, "%s", name);
+}
+
+/* PrintSpacetimeCorr, lmp2sqt.c:677-766 */
+static void write_text(FILE *fp, const sqt_results *r, const sqt_deck *d, int flag_F)
+{
+	const int S = r->nCSpatial, T = r->nCTime;
+	const double *av[3] = { r->avF_qq2, r->avF_s_qq2, r->avF_d_qq2 };
+	const double *sd[3] = { r->StdDevF_qq2, r->StdDevF_s_qq2, r->StdDevF_d_qq2 };
+	fprintf(fp, "%s\n", k_txtCorr);
+	for (int k2 = 0; k2 < 4; k2++) {
+		fprintf(fp, "# %s %7.3f %7.3f %7.3f\n", k_header[k2], r->kVal, (d->nCSkip + 1) * d->deltaT, d->rVal);
+		if (k2 < 3) {
+			if (k2 == 0 || flag_F)
+				for (int nt = 0; nt < T; nt++) {
+					double time_d = nt * 1. * d->deltaT;
+					fprintf(fp, "%7.3f", time_d);
+					for (int nk = 0; nk < S; nk++) fprintf(fp, " %8.4e %8.4e", av[k2][nk * T + nt], sd[k2][nk * T + nt]);
+					fprintf(fp, "\n");
+				}
+		} else {
+			for (int nt = 0; nt < T; nt++) {
+				for (int nr = 0; nr < S; nr++) fprintf(fp, " %8.4e", r->avDrTable[nr * T + nt]);
+				fprintf(fp, "\n");
+			}
+		}
+		fprintf(fp, "\n");
+	}
+}
+
+/* PrintSpacetimeCorr_binary, lmp2sqt.c:768-864 */
+static void write_binary(FILE *fp, const sqt_results *r, const sqt_deck *d, int flag_F)
+{
+	const int S = r->nCSpatial, T = r->nCTime;
+	const double *av[4] = { r->avF_qq2, r->avF_s_qq2, r->avF_d_qq2, r->avDrTable };
+	int nTypes = 4;
+	int header_txtCorr = (int)strlen(k_txtCorr);
+	fwrite(&header_txtCorr, sizeof(int), 1, fp);
+	fwrite(k_txtCorr, 1, header_txtCorr, fp);
+	fwrite(&nTypes, sizeof(int), 1, fp);
+	for (int k2 = 0; k2 < nTypes; k2++) {
+		double col2 = r->kVal, col3 = 1.0 * d->deltaT * (d->nCSkip + 1), col4 = d->rVal;
+		int yes = 1, no = 0;
+		int length = (int)strlen(k_header[k2]);
+		fwrite(&length, sizeof(int), 1, fp);
+		fwrite(k_header[k2], sizeof(char), length, fp);
+		fwrite(&col2, sizeof(double), 1, fp);
+		fwrite(&col3, sizeof(double), 1, fp);
+		fwrite(&col4, sizeof(double), 1, fp);
+		if ((k2 == 1 || k2 == 2) && !flag_F) { fwrite(&no, sizeof(int), 1, fp); continue; }
+		fwrite(&yes, sizeof(int), 1, fp);
+		for (int nt = 0; nt < T; nt++)
+			for (int nk = 0; nk < S; nk++) fwrite(&av[k2][nk * T + nt], sizeof(double), 1, fp);
+	}
+}
+
+/* PrintEtc, lmp2sqt.c:865-1093 (SSF and Dt; the C2_* and Stress files belong to -V/-M/-s) */
+static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, int flag_f, int flag_t, const char *date)
+{
+	const int S = r->nCSpatial, T = r->nCTime;
+	char name[64], fn_Dt[512], fn_SSF[512];
+	int nfile = 0;
+	do { /* first unused index, probed on the Dt name only (lmp2sqt.c:886-902) */
+		snprintf(name, sizeof(name), "Dt%03d.info.%s", nfile, date);
+		join(fn_Dt, sizeof(fn_Dt), dir, name);
+		snprintf(name, sizeof(name), "SSF%03d.info.%s", nfile, date);
+		join(fn_SSF, sizeof(fn_SSF), dir, name);
+		nfile++;
+	} while (0 == access(fn_Dt, F_OK));
+	if (flag_f) {
+		FILE *fp = fopen(fn_SSF, "w");
+		if (!fp) return -1;
+		for (int nk = 0; nk < S; nk++) {
+			double value1 = r->avF_qq2[nk * T + 0];
+			double value2 = sqrt(r->StdDevF_qq2[nk * T + 0] - value1 * value1); /* sic: sigma is already rooted, :996-997 */
+			fprintf(fp, "%8.4f" " %8.4g" " %8.4g" "\n", (nk + 1) * r->kVal, value1, value2);
+		}
+		fclose(fp);
+	}
+	if (flag_t) {
+		FILE *fp = fopen(fn_Dt, "w");
+		if (!fp) return -1;
+		fprintf(fp, "#time MSD msdx msdy msdz D(t) anotherform MQD");
+		fprintf(fp, " MSDCM\n");
+		fprintf(stderr, "print time correlation \n");
+		double *rrDt = (double *)calloc(T > 3 ? T : 3, sizeof(double));
+		const double *msd = r->rrMSDAv;
+		double fac = 1. / (2. * d->deltaT * (d->nCSkip + 1) * DIM * 2);
+		if (T >= 3) {
+			rrDt[0] = fac * (-msd[2] + 4. * msd[1] - 3. * msd[0]);
+			for (int nr = 1; nr < T - 1; nr++) rrDt[nr] = fac * (msd[nr + 1] - msd[nr - 1]);
+			rrDt[T - 1] = fac * (msd[T - 3] - 4. * msd[T - 2] + 3. * msd[T - 1]);
+		}
+		for (int nt = 0; nt < T; nt++) {
+			double tVal = nt * d->deltaT * (d->nCSkip + 1);
+			double anotherDt = 0;
+			if (nt != 0) anotherDt = msd[nt] / (tVal * DIM * 2);
+			fprintf(fp, "%8.4f %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g", tVal, msd[nt], 0., 0., 0., rrDt[nt], anotherDt,
+			        r->rrMQDAv[nt]);
+			fprintf(fp, " %8.4f\n", r->rrMSDCMAv[nt]);
+		}
+		free(rrDt);
+		fclose(fp);
+	}
+	return 0;
+}
+
+int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t,
+                           const char *date)
+{
+	char today[32], path[512];
+	if (!date) {
+		time_t raw = time(NULL);
+		strftime(today, sizeof(today), "%y%m%d", localtime(&raw)); /* lmp2sqt.c:127-132 */
+		date = today;
+	}
+	join(path, sizeof(path), dir, "output.log");
+	FILE *flog = fopen(path, "w+");
+	if (!flog) return -1;
+	fputs("Call PrintProcess : \n", flog);
+	sqt_host_normalise(r, d, flag_f, flag_F, flag_t);
+	if (write_etc(dir, r, d, flag_f, flag_t, date)) { fclose(flog); return -1; }
+	if (flag_f) {
+		const char *fout_filename = "output.binary";
+		join(path, sizeof(path), dir, fout_filename);
+		FILE *fout = fopen(path, "w+");
+		join(path, sizeof(path), dir, "output.txt");
+		FILE *ftxt = fopen(path, "w+");
+		if (!fout || !ftxt) { fclose(flog); return -1; }
+		fprintf(flog, "%s %ld %d \n", fout_filename, ftell(fout), r->limitCorrAv);
+		fprintf(stderr, "%s %ld %d \n", fout_filename, ftell(fout), r->limitCorrAv);
+		write_text(ftxt, r, d, flag_F);
+		write_binary(fout, r, d, flag_F);
+		fclose(ftxt);
+		fclose(fout);
+	}
+	fclose(flog);
+	return 0;
+}

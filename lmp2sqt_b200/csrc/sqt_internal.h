@@ -1,0 +1,91 @@
+// sqt_internal.h -- shared declarations between the C-ABI layer (sqt_api.cu), the kernels
+// (sqt_kernels.cu), the NCCL shim (sqt_comm.cpp) and the synthetic source (sqt_synth.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SQT_NVIRT 6          // virtual origin slots: (axis x,y,z) x (Re, Im) of rho(k)
+#define SQT_MAX_WPB 8        // warps per block of the ring kernel
+
+// Everything the per-frame ring kernel needs.  Passed by value.
+struct RingArgs {
+	const double *cur;        // current frame, SoA [3][cur_pitch]
+	double *ring;             // origin positions [n][3][RP]  (slot-minor: a warp reads 32 origins of one particle/axis contiguously)
+	double *partial;          // per-block partial sums [blocks_p][NV][SPAD]
+	int *hist_cur;            // this frame's van Hove counts [B][nCS]   (zeroed by the reduce kernel)
+	const double *invL0;      // [B] 1/L of each buffer's origin frame
+	const long long *thr;     // [nCS+2] bit patterns of the exact bin thresholds (see host: build_thresholds)
+	long long cur_pitch;
+	int n_local;
+	int chunk;                // particles per block
+	int p;                    // processed-frame index within the current input file
+	int T, B, nCS, RP;
+	int V0;                   // first virtual slot (B rounded up to even)
+	int SPAD, NV, CT;         // padded slot count, values per slot (CT + 2), padded chain count (C*G)
+	double invL;              // 1 / L of the current frame
+	float inv_rVal;
+	int varbox;               // some live origin has a different box length than the current frame
+};
+
+struct KernelChoice {
+	int C, G;                 // chains per thread, lane groups per warp
+	int WPB;                  // warps per block
+	int slot_groups;          // gridDim.y
+	int blocks_p;             // gridDim.x
+	int chunk;
+	int SPAD, NV, CT, NSLOT, V0;
+	size_t smem;
+	int regs;                 // registers per thread reported by the runtime
+	int occ;                  // resident blocks per SM
+};
+
+// ---- kernels.cu ---------------------------------------------------------------------------
+// Picks (C, G, grid) for a deck; returns 0 or a cudaError_t.
+int sqt_pick_kernel(int nCS, int B, int n_local, int n_sm, KernelChoice *kc);
+int sqt_launch_ring(const KernelChoice &kc, const RingArgs &a, cudaStream_t st);
+
+struct ReduceArgs {
+	const double *partial;
+	int blocks_p, NV, SPAD, CT, V0;
+	int p, T, B, nCS;
+	int *hist_cur;            // [B][nCS] -> moved into bufHist, then zeroed
+	int *bufHist;             // [B][T][nCS]
+	double *bufFs;            // [B][T][nCS]
+	double *bufMSD, *bufMQD;  // [B][T]
+	double *rho_cur;          // [6 nCS + 3]: rho (marker layout) then sum of positions
+	double *invL0;            // [B]
+	double invL;
+};
+int sqt_launch_reduce(const ReduceArgs &a, cudaStream_t st);
+
+struct CollectiveArgs {
+	const double *rho_cur;    // reduced over shards
+	double *rho0;             // [B][6 nCS]
+	double *sumr0;            // [B][3]
+	double *bufF;             // [B][T][nCS]
+	double *bufMSDCM;         // [B][T]   (never zeroed: cumulative, lmp2sqt.c:1450)
+	int p, T, B, nCS;
+	double inv_n2;            // 1 / N^2
+};
+int sqt_launch_collective(const CollectiveArgs &a, cudaStream_t st);
+
+struct AccumArgs {
+	// completed buffer nb
+	int nb, T, nCS;
+	const double *bufF, *bufFs, *bufMSD, *bufMQD, *bufMSDCM;
+	const int *bufHist;
+	double *cblk;             // packed block [Fs T*nCS | MSD T | MQD T | hist T*nCS]  (allreduced between pack and accumulate)
+	double *av[7];            // avF sdF avFs sdFs avFd sdFd avHist   [nCS][T]
+	double *av1[3];           // msd mqd msdcm [T]
+};
+int sqt_launch_pack(const AccumArgs &a, cudaStream_t st);
+int sqt_launch_accumulate(const AccumArgs &a, cudaStream_t st);
+
+int sqt_launch_soa_copy(double *dst, long long dst_pitch, const double *src, long long src_pitch, int n, cudaStream_t st);
+
+// ---- sqt_comm.cpp -------------------------------------------------------------------------
+struct SqtComm;
+int sqt_comm_get_unique_id(void *out128, char *err, int errlen);
+int sqt_comm_create(SqtComm **out, const void *id128, int rank, int nranks, char *err, int errlen);
+int sqt_comm_allreduce_f64(SqtComm *c, double *buf, size_t count, cudaStream_t st, char *err, int errlen);
+void sqt_comm_destroy(SqtComm *c);

@@ -1,0 +1,337 @@
+"""Python mirror of the reference's call seam over the C-ABI (include/sqt.h).
+
+The reference drives its hot path with four calls::
+
+    InitSpacetimeCorr(cl)      lmp2sqt.c:446     once per input file
+    EvalSpacetimeCorr(cl)      lmp2sqt.c:1599    once per frame, cl->snap = ReadDump(fp)
+    PrintProcess(cl)           lmp2sqt.c:338     when countCorrAv == limitCorrAv, and at end of run
+
+:class:`SpacetimeCorr` exposes exactly those under the same names (plus pythonic aliases), with
+the same argument meaning and the same error behaviour (a malformed frame stops the file; a
+failed allocation aborts), so parity tests read like the reference's main loop.
+All numerics run in the CUDA engine; this module only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import SQT_FLUSH, SqtDeck, SqtParams, SqtResults
+
+NAMES2D = ["avF_qq2", "StdDevF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "avF_d_qq2", "StdDevF_d_qq2", "avDrTable"]
+NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv"]
+
+
+class SqtError(RuntimeError):
+    pass
+
+
+@dataclass
+class Deck:
+    """in.lmp2sqt.* (lmp2sqt.c:82-92)."""
+    kVal: float = 0.0981748
+    deltaT: float = 0.06
+    mass: float = 1.0
+    rVal: float = 0.2
+    limitCorrAv: int = 0
+    nCBuffer: int = 150
+    nCSpatial: int = 30
+    nCTime: int = 150
+    nCSkip: int = 0
+
+    def to_c(self) -> SqtDeck:
+        d = SqtDeck(self.kVal, self.deltaT, self.mass, self.rVal, self.limitCorrAv, self.nCBuffer, self.nCSpatial,
+                    self.nCTime, self.nCSkip)
+        for i in range(9):
+            d.status[i] = 1
+        return d
+
+    @staticmethod
+    def read(path: str) -> "Deck":
+        d = SqtDeck()
+        rc = _lib.host_lib().sqt_deck_read(os.fsencode(path), C.byref(d))
+        if rc < 0:
+            raise FileNotFoundError(path)
+        return Deck(d.kVal, d.deltaT, d.mass, d.rVal, d.limitCorrAv, d.nCBuffer, d.nCSpatial, d.nCTime, d.nCSkip)
+
+
+class Results:
+    """Owner of an ``sqt_results`` (raw sums as the engine returns them; ``normalise`` = prePrintProcess)."""
+
+    def __init__(self, nCSpatial: int, nCTime: int):
+        self.c = SqtResults()
+        rc = _lib.engine_lib().sqt_results_alloc(C.byref(self.c), nCSpatial, nCTime)
+        if rc:
+            raise MemoryError("sqt_results_alloc")
+        self.S, self.T = nCSpatial, nCTime
+
+    def __del__(self):
+        try:
+            _lib.engine_lib().sqt_results_free(C.byref(self.c))
+        except Exception:
+            pass
+
+    def array(self, name: str) -> np.ndarray:
+        p = getattr(self.c, name)
+        shape = (self.S, self.T) if name in NAMES2D else (self.T,)
+        return np.ctypeslib.as_array(p, shape=shape)
+
+    def to_dict(self) -> dict:
+        d = {n: self.array(n).copy() for n in NAMES2D + NAMES1D}
+        for k in ("countCorrAv", "limitCorrAv", "nPtls", "g_Vol", "kVal", "first_Vol", "first_limitCorrAv", "number_call_print"):
+            d[k] = getattr(self.c, k)
+        return d
+
+    def normalise(self, deck: Deck, flags: str = "Ft") -> None:
+        """prePrintProcess (lmp2sqt.c:576-675), in place."""
+        f_F = "F" in flags
+        dk = deck.to_c()
+        _lib.host_lib().sqt_host_normalise(C.byref(self.c), C.byref(dk), int(f_F or "f" in flags), int(f_F), int("t" in flags))
+
+    def print_process(self, outdir: str, deck: Deck, flags: str = "Ft", date: str | None = None) -> None:
+        """PrintProcess (lmp2sqt.c:338-367): normalise in place and write the reference's files into ``outdir``."""
+        f_F = "F" in flags
+        dk = deck.to_c()
+        rc = _lib.host_lib().sqt_host_print_process(os.fsencode(outdir), C.byref(self.c), C.byref(dk),
+                                                    int(f_F or "f" in flags), int(f_F), int("t" in flags),
+                                                    date.encode() if date else None)
+        if rc:
+            raise OSError("sqt_host_print_process failed in %s" % outdir)
+
+
+class SpacetimeCorr:
+    """One GPU's share of the space-time correlation state (the reference's MakeSqtClass + globals)."""
+
+    def __init__(self, deck: Deck, flags: str = "Ft", device: int = 0):
+        self.lib = _lib.engine_lib()
+        self.deck = deck
+        self.flags = flags
+        f_F = "F" in flags
+        p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
+                      deck.nCTime, deck.nCSkip, int(f_F or "f" in flags), int(f_F), int("t" in flags), device)
+        h = C.c_void_p()
+        rc = self.lib.sqt_create(C.byref(p), C.byref(h))
+        if rc:
+            raise SqtError("sqt_create failed (%d): %s" % (rc, self.lib.sqt_last_error(None).decode()))
+        self.h = h
+        self.S, self.T = deck.nCSpatial, deck.nCTime
+        self.B = max(1, min(deck.nCBuffer, deck.nCTime))
+        self.device = device
+
+    # ---- lifecycle -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sqt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> int:
+        if rc < 0:
+            raise SqtError("%s failed (%d): %s" % (what, rc, self.lib.sqt_last_error(self.h).decode()))
+        return rc
+
+    # ---- the reference seam ----------------------------------------------------------------
+    def set_limit(self, limitCorrAv: int):
+        self._check(self.lib.sqt_set_limit(self.h, int(limitCorrAv)), "sqt_set_limit")
+
+    def InitSpacetimeCorr(self):
+        self._check(self.lib.sqt_begin_file(self.h), "sqt_begin_file")
+
+    begin_file = InitSpacetimeCorr
+
+    def stage(self, n_local: int) -> np.ndarray:
+        """Pinned SoA staging for the next frame as a (3, n) float64 view."""
+        p = self.lib.sqt_stage_acquire(self.h, int(n_local))
+        if not p:
+            raise SqtError("sqt_stage_acquire: " + self.lib.sqt_last_error(self.h).decode())
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(3, n_local))
+
+    def EvalSpacetimeCorr(self, xyz: np.ndarray, xlo: float, xhi: float, n_total: int | None = None) -> int:
+        """One frame.  ``xyz`` is (n, 3) atoms in dump order (this rank's shard).  Returns SQT_FLUSH (1)
+        when the reference would have called PrintProcess inside AccumSpacetimeCorr."""
+        n = xyz.shape[0]
+        st = self.stage(n)
+        st[:] = np.asarray(xyz, dtype=np.float64).T
+        return self.push_staged(st, n, n_total if n_total is not None else n, xlo, xhi)
+
+    push_frame = EvalSpacetimeCorr
+
+    def push_staged(self, st: np.ndarray, n_local: int, n_total: int, xlo: float, xhi: float) -> int:
+        return self._check(self.lib.sqt_push_frame(self.h, st.ctypes.data, int(n_local), int(n_total), float(xlo), float(xhi)),
+                           "sqt_push_frame")
+
+    def push_device(self, dptr: int, n_local: int, n_total: int, xlo: float, xhi: float) -> int:
+        return self._check(self.lib.sqt_push_frame_device(self.h, C.c_void_p(dptr), int(n_local), int(n_total), float(xlo), float(xhi)),
+                           "sqt_push_frame_device")
+
+    def fetch(self) -> Results:
+        r = Results(self.S, self.T)
+        self._check(self.lib.sqt_fetch_results(self.h, C.byref(r.c)), "sqt_fetch_results")
+        return r
+
+    def finish(self) -> Results | None:
+        """End of run (lmp2sqt.c:327-333): results to print, or None if a mid-run print already happened."""
+        r = Results(self.S, self.T)
+        rc = self._check(self.lib.sqt_finish(self.h, C.byref(r.c)), "sqt_finish")
+        return r if rc == 1 else None
+
+    def PrintProcess(self, outdir: str, results: Results | None = None, date: str | None = None) -> Results:
+        r = results if results is not None else self.fetch()
+        r.print_process(outdir, self.deck, self.flags, date)
+        return r
+
+    # ---- introspection ---------------------------------------------------------------------
+    def sync(self):
+        self._check(self.lib.sqt_sync(self.h), "sqt_sync")
+
+    @property
+    def countCorrAv(self) -> int:
+        return self.lib.sqt_count_corr_av(self.h)
+
+    @property
+    def number_call_print(self) -> int:
+        return self.lib.sqt_number_call_print(self.h)
+
+    def buffer_counts(self):
+        return [self.lib.sqt_buffer_count(self.h, nb) for nb in range(self.B)]
+
+    def rho(self) -> np.ndarray:
+        out = np.zeros((3, self.S, 2))
+        self._check(self.lib.sqt_get_rho(self.h, out.ctypes.data), "sqt_get_rho")
+        return out
+
+    @property
+    def kernel_launches(self) -> int:
+        return self.lib.sqt_kernel_launches(self.h)
+
+    @property
+    def kernel_config(self) -> str:
+        return self.lib.sqt_kernel_config(self.h).decode()
+
+    def profile(self, on: bool):
+        self.lib.sqt_profile_enable(self.h, int(on))
+
+    def profile_read(self):
+        n, ms = C.c_longlong(), C.c_double()
+        self._check(self.lib.sqt_profile_read(self.h, C.byref(n), C.byref(ms)), "sqt_profile_read")
+        return n.value, ms.value
+
+    def timer_start(self):
+        self._check(self.lib.sqt_timer_start(self.h), "sqt_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.sqt_timer_stop(self.h, C.byref(ms)), "sqt_timer_stop")
+        return ms.value
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, _lib.SQT_COMM_ID_BYTES)
+        self._check(self.lib.sqt_comm_init(self.h, buf, rank, nranks), "sqt_comm_init")
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(_lib.SQT_COMM_ID_BYTES)
+    rc = _lib.engine_lib().sqt_comm_unique_id(buf)
+    if rc:
+        raise SqtError("sqt_comm_unique_id failed: " + _lib.engine_lib().sqt_last_error(None).decode())
+    return buf.raw
+
+
+class SynthSource:
+    """On-device synthetic frame source (include/sqt.h, sqt_synth_*)."""
+
+    def __init__(self, n_cells: int, first_atom: int, n_local: int, seed: int = 20261019, device: int = 0):
+        self.lib = _lib.engine_lib()
+        h = C.c_void_p()
+        rc = self.lib.sqt_synth_create(device, n_cells, first_atom, n_local, seed, C.byref(h))
+        if rc:
+            raise SqtError("sqt_synth_create failed (%d)" % rc)
+        self.h = h
+        self.n_local = n_local
+        self.n_total = 4 * n_cells ** 3
+        self.L = self.lib.sqt_synth_box_length(h)
+
+    def next(self) -> int:
+        p = self.lib.sqt_synth_next(self.h)
+        if not p:
+            raise SqtError("sqt_synth_next failed")
+        return p
+
+    def to_host(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((3, self.n_local))
+        rc = self.lib.sqt_synth_copy_to_host(self.h, out.ctypes.data)
+        if rc:
+            raise SqtError("sqt_synth_copy_to_host failed")
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sqt_synth_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure_dfma_peak(device: int = 0):
+    tf, mhz = C.c_double(), C.c_double()
+    rc = _lib.engine_lib().sqt_measure_dfma_peak(device, C.byref(tf), C.byref(mhz))
+    if rc:
+        raise SqtError("sqt_measure_dfma_peak failed (%d)" % rc)
+    return tf.value, mhz.value
+
+
+def shard_bounds(n_total: int, rank: int, nranks: int) -> tuple[int, int]:
+    """Particle shard [lo, hi) of ``rank``: contiguous in dump order."""
+    lo = (n_total * rank) // nranks
+    hi = (n_total * (rank + 1)) // nranks
+    return lo, hi
+
+
+def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank: int = 0, nranks: int = 1,
+                     unique_id: bytes | None = None, on_flush=None):
+    """Drive the engine over a list of trajectories (= input files) exactly like the reference's main
+    (lmp2sqt.c:200-333), including its limitCorrAv bookkeeping.  Returns (printed Results | None, engine)."""
+    B = max(1, min(deck.nCBuffer, deck.nCTime))
+    limit = deck.limitCorrAv
+    use = []
+    for t in trajs:
+        n_snap = t.n_frames
+        ok = n_snap >= 5 and int((n_snap - deck.nCTime) / (deck.nCTime // B)) >= 1  # lmp2sqt.c:221-237
+        use.append(ok)
+        if ok:
+            limit += (n_snap - deck.nCTime) // (deck.nCTime // B)                    # lmp2sqt.c:244
+    eng = SpacetimeCorr(deck, flags, device)
+    if nranks > 1:
+        eng.comm_init(unique_id, rank, nranks)
+    eng.set_limit(limit)
+    printed = None
+    for t, u in zip(trajs, use):
+        if not u:
+            continue
+        eng.InitSpacetimeCorr()
+        lo, hi = shard_bounds(t.n_atoms, rank, nranks)
+        for f in range(t.n_frames):
+            rc = eng.EvalSpacetimeCorr(t.positions[f, lo:hi], t.box[f, 0, 0], t.box[f, 0, 1], n_total=t.n_atoms)
+            if rc == SQT_FLUSH:
+                printed = eng.fetch()
+                if on_flush:
+                    on_flush(printed)
+    fin = eng.finish()
+    if fin is not None:
+        printed = fin
+    return printed, eng

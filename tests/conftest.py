@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the oracle restatement (and nothing else) if it is missing; the CUDA extension is built by
+    __graft_entry__.build() and must already be there for the gpu tests -- they fail loudly otherwise."""
+    import pyoracle
+    pyoracle.build()
+    yield

@@ -1,0 +1,139 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes -> libsqt_b200.so), against
+the CPU oracle (oracle/sqt_oracle.c, itself pinned bit-for-bit to the unmodified reference by
+tests/test_oracle.py) on the same seeded frames."""
+import numpy as np
+import pytest
+
+import pyoracle
+from lmp2sqt_b200 import Deck, run_trajectories, synth
+from parity import check_raw_sums, fd_identity
+
+pytestmark = pytest.mark.gpu
+
+BIG = 10**6  # limitCorrAv that is never reached: compare the raw sums of the whole run
+
+
+def _run_both(trajs, S, T, B, skip=0, flags="Ft", rVal=0.2):
+    deck = Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T, nCSkip=skip, rVal=rVal)
+    eng_res, eng = run_trajectories(trajs, deck, flags)
+    got = eng_res.to_dict()
+    _, raw, log = pyoracle.run_port(None, S, T, B, nCSkip=skip, rVal=rVal, limitCorrAv=BIG, files=trajs, flags=flags, finish=False)
+    return got, raw, eng, log
+
+
+@pytest.mark.parametrize("S,T,B,ncell,frames", [
+    (4, 10, 5, 2, 40),      # the smoke shape
+    (10, 30, 30, 3, 100),   # smallQ-like, B == T
+    (30, 12, 4, 2, 50),     # in.lmp2sqt.150's nCSpatial (C=30 kernel)
+    (7, 9, 9, 2, 31),       # odd sizes, padded chains
+])
+def test_ring_matches_oracle(S, T, B, ncell, frames):
+    traj = synth.make_trajectory(n_cells=ncell, n_frames=frames, seed=11)
+    got, raw, eng, _ = _run_both([traj], S, T, B)
+    check_raw_sums(got, raw, traj.n_atoms, label="S%d T%d B%d " % (S, T, B))
+    fd_identity(got)
+
+
+@pytest.mark.parametrize("S", [43, 64, 86, 100, 128, 171])
+def test_large_nCSpatial_lane_groups(S):
+    """nCSpatial 86 / 128 / 171 are the BASELINE configs 3-5 (K = 258 / 384 / 513); above 86 the m-range is
+    split over lane groups with the recurrence state handed through shuffles."""
+    traj = synth.make_trajectory(n_cells=2, n_atoms=29, n_frames=30, seed=5)
+    got, raw, eng, _ = _run_both([traj], S, 8, 8)
+    check_raw_sums(got, raw, traj.n_atoms, label="S%d " % S)
+    fd_identity(got)
+
+
+def test_ragged_skip_two_files_varbox():
+    """Ragged atom count, nCSkip, two input files (ring reset, averages persist), fluctuating box."""
+    t1 = synth.make_trajectory(n_cells=3, n_atoms=50, n_frames=37, seed=3, box_jitter=0.01)
+    t2 = synth.make_trajectory(n_cells=3, n_atoms=50, n_frames=29, seed=4, box_jitter=0.01)
+    got, raw, eng, log = _run_both([t1, t2], 6, 8, 8, skip=1)
+    check_raw_sums(got, raw, 50, label="two files ")
+
+
+def test_bookkeeping_is_exact():
+    """countCorrAv and every TBuf.count after every frame equal the reference state machine's."""
+    from lmp2sqt_b200 import SpacetimeCorr
+    traj = synth.make_trajectory(n_cells=2, n_frames=45, seed=2)
+    S, T, B, skip = 3, 10, 4, 1
+    eng = SpacetimeCorr(Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T, nCSkip=skip))
+    ora = pyoracle.OraclePort(S, T, B, skip, limitCorrAv=BIG)
+    eng.InitSpacetimeCorr(); ora.begin_file()
+    for f in range(traj.n_frames):
+        eng.EvalSpacetimeCorr(traj.positions[f], 0.0, traj.box[f, 0, 1])
+        ora.push_frame(traj.positions[f], 0.0, traj.box[f, 0, 1])
+        assert eng.countCorrAv == ora.countCorrAv
+        assert eng.buffer_counts() == ora.buffer_counts()
+    eng.close()
+
+
+def test_rho_matches_oracle_each_frame():
+    from lmp2sqt_b200 import SpacetimeCorr
+    traj = synth.make_trajectory(n_cells=3, n_frames=6, seed=9)
+    S = 12
+    eng = SpacetimeCorr(Deck(limitCorrAv=BIG, nCBuffer=2, nCSpatial=S, nCTime=4))
+    ora = pyoracle.OraclePort(S, 4, 2, limitCorrAv=BIG)
+    eng.InitSpacetimeCorr(); ora.begin_file()
+    for f in range(traj.n_frames):
+        eng.EvalSpacetimeCorr(traj.positions[f], 0.0, traj.box[f, 0, 1])
+        ora.push_frame(traj.positions[f], 0.0, traj.box[f, 0, 1])
+        np.testing.assert_allclose(eng.rho(), ora.rho(), rtol=0, atol=1e-10 * traj.n_atoms)
+    eng.close()
+
+
+def test_midrun_flush_matches_oracle():
+    """limitCorrAv reached mid-run: results latched at that frame, averages zeroed, later buffers accumulate
+    into fresh sums, end-of-run print suppressed (lmp2sqt.c:438-440, 366, 327)."""
+    traj = synth.make_trajectory(n_cells=2, n_frames=40, seed=1)
+    S, T, B = 4, 10, 5
+    deck = Deck(limitCorrAv=0, nCBuffer=B, nCSpatial=S, nCTime=T)   # + computed 15
+    flushed = []
+    res, eng = run_trajectories([traj], deck, "Ft", on_flush=lambda r: flushed.append(r.to_dict()))
+    assert len(flushed) == 1 and flushed[0]["countCorrAv"] == 15
+    assert eng.number_call_print == 1
+    printed, raw, log = pyoracle.run_port(traj, S, T, B, limitCorrAv=0)
+    assert printed["countCorrAv"] == 15
+    # normalise the engine's latched sums on the host and compare with what the oracle "printed"
+    res.normalise(deck, "Ft")
+    got = res.to_dict()
+    for g, r in [("avF_qq2", "avF"), ("avF_s_qq2", "avF_s"), ("avF_d_qq2", "avF_d"), ("rrMSDAv", "rrMSDAv"), ("rrMQDAv", "rrMQDAv")]:
+        np.testing.assert_allclose(got[g], printed[r], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got["avDrTable"], printed["avDrTable"], rtol=1e-12)
+    # one more buffer completed after the flush and sits in the fresh sums
+    assert eng.countCorrAv == raw["countCorrAv"] == 1
+
+
+def test_known_answers_static_and_translation():
+    """KATs of SURVEY.md section 4: static trajectory (F_s = 1, MSD = 0, all displacements in bin 0) and rigid
+    translation (F_s(q_m, tau) = 1/3 sum_a cos(m k0 d_a tau), MSD = |d|^2 tau^2)."""
+    S, T, B = 5, 6, 6
+    t = synth.static_trajectory(2, 20)
+    deck = Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res, eng = run_trajectories([t], deck)
+    g = res.to_dict(); cnt = g["countCorrAv"]; N = t.n_atoms
+    np.testing.assert_allclose(g["avF_s_qq2"], 3.0 * N * cnt, rtol=1e-13)
+    assert np.all(g["rrMSDAv"] == 0) and np.all(g["rrMQDAv"] == 0)
+    assert np.all(g["avDrTable"][0] == N * cnt) and np.all(g["avDrTable"][1:] == 0)
+    np.testing.assert_allclose(g["avF_qq2"], g["avF_qq2"][:, :1] * np.ones((1, T)), rtol=1e-12)
+    d = (0.1, 0.02, 0.0); Lb = 10.0
+    t = synth.translating_trajectory(50, 25, d=d, box_len=Lb)
+    res, eng = run_trajectories([t], deck)
+    g = res.to_dict(); cnt = g["countCorrAv"]; N = 50
+    k0 = 2 * np.pi / Lb
+    m = np.arange(1, S + 1)[:, None]; tau = np.arange(T)[None, :]
+    want = sum(np.cos(m * k0 * da * tau) for da in d) * N * cnt
+    np.testing.assert_allclose(g["avF_s_qq2"], want, rtol=1e-9, atol=1e-9 * N * cnt)
+    np.testing.assert_allclose(g["rrMSDAv"], (d[0]**2 + d[1]**2) * tau[0]**2 * N * cnt, rtol=1e-9, atol=1e-12)
+
+
+def test_cubic_lattice_structure_factor():
+    """Simple-cubic lattice n^3, L = n a: S(q_m) = N if n | m else 0."""
+    n = 4
+    t = synth.cubic_lattice_trajectory(n, 12)
+    S, T, B = 9, 4, 2
+    res, eng = run_trajectories([t], Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T))
+    g = res.to_dict(); cnt = g["countCorrAv"]; N = n**3
+    Sq = g["avF_qq2"][:, 0] / (3.0 * N * cnt)
+    want = np.array([N if (m % n == 0) else 0.0 for m in range(1, S + 1)])
+    np.testing.assert_allclose(Sq, want, atol=1e-9 * N)
