@@ -97,8 +97,9 @@ int  sqt_begin_file(sqt_handle *h);
 double *sqt_stage_acquire(sqt_handle *h, int n_atoms_local);
 
 /* EvalSpacetimeCorr (lmp2sqt.c:1599-1650) for one frame.  `soa` is either a buffer from
- * sqt_stage_acquire (async H2D, no extra copy) or any host memory (copied synchronously into
- * staging first).  n_atoms_local = atoms this handle owns (its particle shard, dump order);
+ * sqt_stage_acquire (async H2D, no extra copy), or page-locked host memory of the caller
+ * (cudaHostAlloc / cudaHostRegister: async H2D straight from it -- it must stay unmodified until
+ * two further pushes or sqt_sync), or pageable host memory (copied synchronously into staging).  n_atoms_local = atoms this handle owns (its particle shard, dump order);
  * n_atoms_total = atoms in the frame over all shards.  xlo/xhi = x box bounds (L, kVal and
  * g_Vol derive from x only, lmp2sqt.c:1620-1632).
  * Returns SQT_OK, SQT_FLUSH, or <0. */
@@ -158,6 +159,8 @@ const double *sqt_synth_next(sqt_synth *s);
 double sqt_synth_box_length(const sqt_synth *s);
 /* Copies the current frame into host memory (SoA, 3*n doubles). */
 int  sqt_synth_copy_to_host(sqt_synth *s, double *dst);
+/* Copies the current frame into another device buffer (SoA, 3*n doubles) on the same device. */
+int  sqt_synth_copy_to_device(sqt_synth *s, double *d_dst);
 void sqt_synth_destroy(sqt_synth *s);
 
 /* ---- roofline denominator: measured non-tensor FP64 FMA throughput ----------------------- */

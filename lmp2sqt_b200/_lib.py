@@ -79,6 +79,7 @@ ENGINE_API = [
     ("sqt_synth_next", C.c_void_p, [C.c_void_p]),
     ("sqt_synth_box_length", C.c_double, [C.c_void_p]),
     ("sqt_synth_copy_to_host", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("sqt_synth_copy_to_device", C.c_int, [C.c_void_p, C.c_void_p]),
     ("sqt_synth_destroy", None, [C.c_void_p]),
     ("sqt_measure_dfma_peak", C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]

@@ -435,12 +435,18 @@ static int push_common(sqt_handle *h, const double *src, bool on_device, int n_l
 		const double *stage = src;
 		if (src == h->h_stage[0] && h->stage_cap) slot = 0;
 		else if (src == h->h_stage[1] && h->stage_cap) slot = 1;
-		else { // foreign host memory: one extra host copy into pinned staging
-			double *st = sqt_stage_acquire(h, n_local);
-			if (!st) return SQT_ERR_CUDA;
-			memcpy(st, src, sizeof(double) * 3 * (size_t)n_local);
-			stage = st;
-			slot = (st == h->h_stage[0]) ? 0 : 1;
+		else {
+			cudaPointerAttributes pa;
+			bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+			cudaGetLastError(); // pageable memory makes the query fail on some drivers: not an error here
+			if (pinned) { slot = h->stage_next; h->stage_next ^= 1; }
+			else { // pageable host memory: one extra host copy into pinned staging
+				double *st = sqt_stage_acquire(h, n_local);
+				if (!st) return SQT_ERR_CUDA;
+				memcpy(st, src, sizeof(double) * 3 * (size_t)n_local);
+				stage = st;
+				slot = (st == h->h_stage[0]) ? 0 : 1;
+			}
 		}
 		// cur[slot] is free once the ring kernel that read it two frames ago has run
 		CU(cudaStreamWaitEvent(h->s_copy, h->ev_ring[slot], 0));

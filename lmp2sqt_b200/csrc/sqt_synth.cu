@@ -117,6 +117,13 @@ extern "C" int sqt_synth_copy_to_host(sqt_synth *s, double *dst)
 	return cudaMemcpy(dst, s->d_pos, sizeof(double) * 3 * (size_t)s->n_local, cudaMemcpyDeviceToHost) == cudaSuccess ? SQT_OK : SQT_ERR_CUDA;
 }
 
+extern "C" int sqt_synth_copy_to_device(sqt_synth *s, double *d_dst)
+{
+	if (!s || !d_dst) return SQT_ERR_ARG;
+	cudaSetDevice(s->device);
+	return cudaMemcpyAsync(d_dst, s->d_pos, sizeof(double) * 3 * (size_t)s->n_local, cudaMemcpyDeviceToDevice, 0) == cudaSuccess ? SQT_OK : SQT_ERR_CUDA;
+}
+
 extern "C" void sqt_synth_destroy(sqt_synth *s)
 {
 	if (!s) return;

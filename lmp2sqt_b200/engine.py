@@ -275,6 +275,11 @@ class SynthSource:
             raise SqtError("sqt_synth_copy_to_host failed")
         return out
 
+    def to_device(self, dptr: int) -> None:
+        rc = self.lib.sqt_synth_copy_to_device(self.h, C.c_void_p(dptr))
+        if rc:
+            raise SqtError("sqt_synth_copy_to_device failed")
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.sqt_synth_destroy(self.h)

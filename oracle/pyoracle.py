@@ -397,3 +397,51 @@ def parse_output_binary(path, nCSpatial, nCTime) -> dict:
 if __name__ == "__main__":
     build(force=True)
     print(json.dumps({"port": os.path.exists(PORT_SO), "reference": have_reference()}))
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline for bench.py: the unmodified reference timed on a bounded sample of a workload.
+# ----------------------------------------------------------------------------------------------
+def _bench_worker(job_path: str) -> None:
+    with open(job_path, "rb") as f:
+        job = pickle.load(f)
+    os.chdir(job["cwd"])
+    S, T, B, n = job["S"], job["T"], job["B"], job["n_atoms"]
+    ref = ReferenceLib(S, T, B, 0, 0.2, flags="Ft")
+    ref.set_limit(10**9)
+    rng = np.random.Generator(np.random.PCG64(job["seed"]))
+    L = float((n / 0.8442) ** (1.0 / 3.0))
+    pos = rng.uniform(0.0, L, size=(n, 3))
+    ref.begin_file()
+    times = []
+    total = job["fill"] + job["warmup"] + job["steps"]
+    for f in range(total):
+        pos = pos + rng.normal(0.0, 0.077, size=(n, 3))
+        times.append(ref.push_frame(pos, 0.0, L))
+    with open(job["out"], "wb") as f:
+        pickle.dump({"times": times, "countCorrAv": ref.countCorrAv}, f)
+
+
+def bench_reference(n_atoms, S, T, B, fill, warmup, steps, threads, seed=1, timeout=1500) -> dict:
+    """Time the reference's own EvalSpacetimeCorr (lmp2sqt.c:1599) frame by frame on ``n_atoms`` random-walk
+    atoms: ``fill`` frames to fill the origin ring (untimed), ``warmup`` + ``steps`` steady-state frames.
+    OMP_NUM_THREADS=``threads``.  Returns per-frame wall seconds of the timed steps."""
+    if not have_reference():
+        raise RuntimeError("oracle/_ref not built")
+    with tempfile.TemporaryDirectory() as td:
+        job = dict(cwd=td, out=os.path.join(td, "o.pkl"), S=S, T=T, B=B, n_atoms=n_atoms, fill=fill, warmup=warmup,
+                   steps=steps, seed=seed)
+        jp = os.path.join(td, "job.pkl")
+        with open(jp, "wb") as f:
+            pickle.dump(job, f)
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        code = "import sys; sys.path.insert(0, %r); import pyoracle; pyoracle._bench_worker(%r)" % (HERE, jp)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0:
+            raise RuntimeError("reference bench worker failed:\n" + r.stdout[-1500:] + r.stderr[-1500:])
+        with open(job["out"], "rb") as f:
+            out = pickle.load(f)
+    t = out["times"]
+    out["fill_s"] = float(sum(t[:fill]))
+    out["step_times"] = t[fill + warmup:]
+    return out
