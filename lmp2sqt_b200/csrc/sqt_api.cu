@@ -350,7 +350,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	const bool split = h->s_coll != h->s_main;
 	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0)); // previous frame's collective stage
 	ReduceArgs rr;
-	rr.partial = h->d_partial; rr.blocks_p = h->kc.blocks_p; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0;
+	rr.partial = h->d_partial; rr.blocks_p = h->kc.blocks_p; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
 	rr.p = p; rr.T = T; rr.B = B; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
 	rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.rho_cur = h->d_rho_cur; rr.invL0 = h->d_invL0; rr.invL = invL;
 	rc = sqt_launch_reduce(rr, h->s_main);

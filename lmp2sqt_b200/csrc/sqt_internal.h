@@ -5,7 +5,7 @@
 #include <stdint.h>
 
 #define SQT_NVIRT 6          // virtual origin slots: (axis x,y,z) x (Re, Im) of rho(k)
-#define SQT_MAX_WPB 8        // warps per block of the ring kernel
+#define SQT_MAX_WPB 4        // warps per block of the ring kernel
 
 // Everything the per-frame ring kernel needs.  Passed by value.
 struct RingArgs {
@@ -21,7 +21,7 @@ struct RingArgs {
 	int p;                    // processed-frame index within the current input file
 	int T, B, nCS, RP;
 	int V0;                   // first virtual slot (B rounded up to even)
-	int SPAD, NV, CT;         // padded slot count, values per slot (CT + 2), padded chain count (C*G)
+	int SPAD, NV, CT;         // padded slot count, values per slot (CT + 2 G), padded chain count (C*G)
 	double invL;              // 1 / L of the current frame
 	float inv_rVal;
 	int varbox;               // some live origin has a different box length than the current frame
@@ -46,7 +46,7 @@ int sqt_launch_ring(const KernelChoice &kc, const RingArgs &a, cudaStream_t st);
 
 struct ReduceArgs {
 	const double *partial;
-	int blocks_p, NV, SPAD, CT, V0;
+	int blocks_p, NV, SPAD, CT, V0, G;
 	int p, T, B, nCS;
 	int *hist_cur;            // [B][nCS] -> moved into bufHist, then zeroed
 	int *bufHist;             // [B][T][nCS]

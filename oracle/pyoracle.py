@@ -75,10 +75,15 @@ class OraclePort:
         L.sqt_oracle_buffer_count.argtypes = [C.c_void_p, C.c_int]
         L.sqt_oracle_kVal.argtypes = [C.c_void_p]
         L.sqt_oracle_kVal.restype = C.c_double
-        for fn in ("raw2d", "printed2d", "raw1d", "printed1d"):
+        for fn in ("raw2d", "printed2d", "raw1d", "printed1d", "printed_raw2d", "printed_raw1d"):
             f = getattr(L, "sqt_oracle_" + fn)
             f.argtypes = [C.c_void_p, C.c_int]
             f.restype = C.POINTER(C.c_double)
+        for fn in ("first_vol", "vol"):
+            f = getattr(L, "sqt_oracle_" + fn)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_double
+        L.sqt_oracle_first_limit.argtypes = [C.c_void_p]
         for fn in ("factorDr", "rho"):
             f = getattr(L, "sqt_oracle_" + fn)
             f.argtypes = [C.c_void_p]
@@ -143,6 +148,15 @@ class OraclePort:
         d["kVal"] = self.kVal
         return d
 
+    def printed_raw(self) -> dict:
+        """Raw sums at the moment of the last print + the scalars the host normalisation needs."""
+        d = {n: self._arr("printed_raw2d", i, (self.S, self.T)) for i, n in enumerate(NAMES2D)}
+        d.update({n: self._arr("printed_raw1d", i, (self.T,)) for i, n in enumerate(NAMES1D)})
+        d.update(countCorrAv=self.printed_count, kVal=self.kVal, nPtls=self.L.sqt_oracle_nPtls(self.h),
+                 first_Vol=self.L.sqt_oracle_first_vol(self.h), first_limitCorrAv=self.L.sqt_oracle_first_limit(self.h),
+                 g_Vol=self.L.sqt_oracle_vol(self.h), limitCorrAv=self.L.sqt_oracle_limitCorrAv(self.h))
+        return d
+
     def rho(self):
         return np.ctypeslib.as_array(self.L.sqt_oracle_rho(self.h), shape=(3, self.S, 2)).copy()
 
@@ -182,9 +196,12 @@ def run_port(traj, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=
             log.append((o.countCorrAv, tuple(o.buffer_counts())))
             if rc == 1:
                 printed = o.printed()
+                printed["_raw_at_print"] = o.printed_raw()
     raw = o.raw()
     if finish and o.finish():
         printed = o.printed()
+    if printed is not None:
+        printed["_raw_at_print"] = o.printed_raw()
     return printed, raw, log
 
 

@@ -50,8 +50,9 @@ struct sqt_oracle {
 	double *rho, *tmp_row, *self, *dist;
 	const double *cur_xyz;
 	/* running sums: 0 avF 1 StdDevF 2 avF_s 3 StdDevF_s 4 avF_d 5 StdDevF_d 6 avDrTable */
-	double *sum2d[7], *out2d[7];
-	double *sum1d[3], *out1d[3]; /* 0 MSD 1 MQD 2 MSDCM */
+	double *sum2d[7], *out2d[7], *rawp2d[7]; /* running sums, normalised at last print, raw at last print */
+	double *sum1d[3], *out1d[3], *rawp1d[3]; /* 0 MSD 1 MQD 2 MSDCM */
+	double first_vol; int first_limit;
 	double *factorDr;
 };
 
@@ -75,8 +76,8 @@ sqt_oracle *sqt_oracle_create(const sqt_oracle_params *p)
 		b->msd = zalloc(T); b->mqd = zalloc(T); b->msdcm = zalloc(T);
 		b->org_rho = zalloc(2 * NAX * S);
 	}
-	for (int i = 0; i < 7; i++) { o->sum2d[i] = zalloc((size_t)S * T); o->out2d[i] = zalloc((size_t)S * T); }
-	for (int i = 0; i < 3; i++) { o->sum1d[i] = zalloc(T); o->out1d[i] = zalloc(T); }
+	for (int i = 0; i < 7; i++) { o->sum2d[i] = zalloc((size_t)S * T); o->out2d[i] = zalloc((size_t)S * T); o->rawp2d[i] = zalloc((size_t)S * T); }
+	for (int i = 0; i < 3; i++) { o->sum1d[i] = zalloc(T); o->out1d[i] = zalloc(T); o->rawp1d[i] = zalloc(T); }
 	o->rho = zalloc(2 * NAX * S);
 	o->tmp_row = zalloc(2 * NAX * S);
 	o->factorDr = zalloc(S);
@@ -92,8 +93,8 @@ void sqt_oracle_destroy(sqt_oracle *o)
 		free(b->msdcm); free(b->org_rho); free(b->org_pos); free(b->org_self); free(b->org_dist);
 	}
 	free(o->buf);
-	for (int i = 0; i < 7; i++) { free(o->sum2d[i]); free(o->out2d[i]); }
-	for (int i = 0; i < 3; i++) { free(o->sum1d[i]); free(o->out1d[i]); }
+	for (int i = 0; i < 7; i++) { free(o->sum2d[i]); free(o->out2d[i]); free(o->rawp2d[i]); }
+	for (int i = 0; i < 3; i++) { free(o->sum1d[i]); free(o->out1d[i]); free(o->rawp1d[i]); }
 	free(o->rho); free(o->tmp_row); free(o->self); free(o->dist); free(o->factorDr);
 	free(o);
 }
@@ -257,8 +258,8 @@ static void print_process(sqt_oracle *o)
 	double inverseNptls = 1. / N;
 	double inverseNptlsSq = 1. / (N * N);
 	double average_number = 1. / (3.0 * o->countCorrAv);
-	for (int i = 0; i < 7; i++) memcpy(o->out2d[i], o->sum2d[i], sizeof(double) * S * T);
-	for (int i = 0; i < 3; i++) memcpy(o->out1d[i], o->sum1d[i], sizeof(double) * T);
+	for (int i = 0; i < 7; i++) { memcpy(o->out2d[i], o->sum2d[i], sizeof(double) * S * T); memcpy(o->rawp2d[i], o->sum2d[i], sizeof(double) * S * T); }
+	for (int i = 0; i < 3; i++) { memcpy(o->out1d[i], o->sum1d[i], sizeof(double) * T); memcpy(o->rawp1d[i], o->sum1d[i], sizeof(double) * T); }
 	if (o->p.flag_f) {
 		for (int nr = 0; nr < S; nr++)
 			for (int nt = 0; nt < T; nt++) {
@@ -332,7 +333,7 @@ int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, d
 	if (o->nSkip < o->p.nCSkip) { o->nSkip++; return 0; }
 	o->L = xhi - xlo;
 	o->vol = o->L * o->L * o->L;
-	if (!o->alloc_more) { o->N = n; alloc_more(o); o->alloc_more = 1; }
+	if (!o->alloc_more) { o->N = n; o->first_vol = o->vol; o->first_limit = o->limitCorrAv; alloc_more(o); o->alloc_more = 1; }
 	if (n != o->N) return -1;
 	o->kVal = 2. * M_PI / o->L;
 	o->cur_xyz = xyz;
@@ -369,5 +370,10 @@ const double *sqt_oracle_raw2d(const sqt_oracle *o, int w) { return o->sum2d[w];
 const double *sqt_oracle_printed2d(const sqt_oracle *o, int w) { return o->out2d[w]; }
 const double *sqt_oracle_raw1d(const sqt_oracle *o, int w) { return o->sum1d[w]; }
 const double *sqt_oracle_printed1d(const sqt_oracle *o, int w) { return o->out1d[w]; }
+const double *sqt_oracle_printed_raw2d(const sqt_oracle *o, int w) { return o->rawp2d[w]; }
+const double *sqt_oracle_printed_raw1d(const sqt_oracle *o, int w) { return o->rawp1d[w]; }
+double sqt_oracle_first_vol(const sqt_oracle *o) { return o->first_vol; }
+int sqt_oracle_first_limit(const sqt_oracle *o) { return o->first_limit; }
+double sqt_oracle_vol(const sqt_oracle *o) { return o->vol; }
 const double *sqt_oracle_factorDr(const sqt_oracle *o) { return o->factorDr; }
 const double *sqt_oracle_rho(const sqt_oracle *o) { return o->rho; }

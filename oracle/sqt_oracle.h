@@ -64,6 +64,12 @@ const double *sqt_oracle_printed2d(const sqt_oracle *o, int which);
 /* which: 0 rrMSDAv, 1 rrMQDAv, 2 rrMSDCMAv  (length nCTime) */
 const double *sqt_oracle_raw1d(const sqt_oracle *o, int which);
 const double *sqt_oracle_printed1d(const sqt_oracle *o, int which);
+/* the raw sums as they stood when the last print normalised them (input of prePrintProcess) */
+const double *sqt_oracle_printed_raw2d(const sqt_oracle *o, int which);
+const double *sqt_oracle_printed_raw1d(const sqt_oracle *o, int which);
+double sqt_oracle_first_vol(const sqt_oracle *o);   /* g_Vol at the first processed frame (factorDr input) */
+int sqt_oracle_first_limit(const sqt_oracle *o);    /* limitCorrAv at the first processed frame */
+double sqt_oracle_vol(const sqt_oracle *o);
 const double *sqt_oracle_factorDr(const sqt_oracle *o);   /* lmp2sqt.c:1987-2009 */
 /* current-frame rho(k): [3][nCSpatial][2]  (lmp2sqt.c:1173-1174 marker layout) */
 const double *sqt_oracle_rho(const sqt_oracle *o);

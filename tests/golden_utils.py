@@ -1,0 +1,61 @@
+"""Loading the committed golden cases (tests/golden/<case>/, produced by the unmodified reference:
+tests/golden/make_golden.py)."""
+import gzip
+import io
+import json
+import os
+
+import numpy as np
+
+from lmp2sqt_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(d for d in os.listdir(GOLDEN) if os.path.isdir(os.path.join(GOLDEN, d)))
+
+
+def case_dir(name):
+    return os.path.join(GOLDEN, name)
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, name, "case.json")) as f:
+        c = json.load(f)
+    c["arrays"] = dict(np.load(os.path.join(GOLDEN, name, "arrays.npz")))
+    return c
+
+
+def read_dump_text(text: str) -> synth.Trajectory:
+    """Minimal pure-Python reader of the LAMMPS text dump (test helper; the product reader is C)."""
+    lines = text.split("\n")
+    i = 0
+    pos, box, ts = [], [], []
+    while i < len(lines) and lines[i].startswith("ITEM: TIMESTEP"):
+        ts.append(int(lines[i + 1]))
+        n = int(lines[i + 3])
+        b = [[float(v) for v in lines[i + 5 + a].split()[:2]] for a in range(3)]
+        arr = np.loadtxt(io.StringIO("\n".join(lines[i + 9:i + 9 + n])), ndmin=2)
+        pos.append(arr[:, 2:5])
+        box.append(b)
+        i += 9 + n
+    return synth.Trajectory(np.array(pos), np.array(box), np.array(ts), np.ones(pos[0].shape[0], dtype=np.int32))
+
+
+def case_trajectories(name):
+    d = case_dir(name)
+    out = []
+    for fn in sorted(os.listdir(d)):
+        if fn.startswith("dump") and fn.endswith(".gz"):
+            with gzip.open(os.path.join(d, fn), "rt") as f:
+                out.append(read_dump_text(f.read()))
+    return out
+
+
+def unpack_dumps(name, dst):
+    d = case_dir(name)
+    names = []
+    for fn in sorted(os.listdir(d)):
+        if fn.startswith("dump") and fn.endswith(".gz"):
+            with gzip.open(os.path.join(d, fn), "rb") as f, open(os.path.join(dst, fn[:-3]), "wb") as g:
+                g.write(f.read())
+            names.append(fn[:-3])
+    return names

@@ -1,0 +1,185 @@
+"""Host C code (libsqt_host.so: deck, text-dump reader, normalisation, writers) against the files the
+UNMODIFIED reference wrote (tests/golden/).  No GPU: the raw sums fed to the writers come from the oracle."""
+import ctypes as C
+import filecmp
+import os
+import re
+import shutil
+
+import numpy as np
+import pytest
+
+import pyoracle
+from golden_utils import CASES, case_dir, case_trajectories, load_case, unpack_dumps
+from lmp2sqt_b200 import Deck, Results, _lib, synth
+from lmp2sqt_b200._lib import SqtDeck, SqtFrameHeader
+
+libc = C.CDLL(None)
+libc.fopen.restype = C.c_void_p
+libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+libc.fclose.argtypes = [C.c_void_p]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """Every function include/sqt.h and include/sqt_host.h declare is exported by the built libraries
+    (load + symbol lookup only: no compute call without a GPU)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for header, lib, table in (("sqt.h", _lib.engine_lib(), _lib.ENGINE_API), ("sqt_host.h", _lib.host_lib(), _lib.HOST_API)):
+        text = open(os.path.join(root, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared = set(re.findall(r"\b(sqt_[a-z0-9_]+)\s*\(", text))
+        bound = {n for n, _, _ in table}
+        assert declared == bound, (header, declared ^ bound)
+        for n in declared:
+            assert hasattr(lib, n), n
+
+
+def test_engine_fails_loudly_without_gpu_or_with_bad_args():
+    import torch
+    from lmp2sqt_b200 import SpacetimeCorr, SqtError
+    if not torch.cuda.is_available():
+        with pytest.raises(SqtError, match="no usable CUDA device"):
+            SpacetimeCorr(Deck(nCSpatial=4, nCTime=10, nCBuffer=5))
+    with pytest.raises(SqtError):
+        SpacetimeCorr(Deck(nCSpatial=0, nCTime=10, nCBuffer=5))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_deck_read_and_rewrite_match_reference(name, tmp_path):
+    """GetNameList / UpdateNameList: reading the deck the reference was given and rewriting it with the
+    limitCorrAv main() computed gives byte-for-byte the deck the reference left behind."""
+    c = load_case(name)
+    d = SqtDeck()
+    ok = _lib.host_lib().sqt_deck_read(os.path.join(case_dir(name), "in.lmp2sqt").encode(), C.byref(d))
+    assert (d.nCSpatial, d.nCTime, d.nCBuffer) == (c["S"], c["T"], min(c["B"], c["T"]))
+    assert d.limitCorrAv == c["limit"] and d.nCSkip == (c["skip"] or 0)
+    assert ok == 0   # the "NameList -- data" and "----" lines match no name => "not ok"; main() ignores it (lmp2sqt.c:199)
+    B = d.nCBuffer
+    for t in case_trajectories(name):
+        d.limitCorrAv += (t.n_frames - d.nCTime) // (d.nCTime // B)
+    out = tmp_path / "deck"
+    assert _lib.host_lib().sqt_deck_write(str(out).encode(), C.byref(d)) == 0
+    assert out.read_bytes() == open(os.path.join(case_dir(name), "in.lmp2sqt.after"), "rb").read()
+
+
+def test_deck_missing_file_and_template(tmp_path):
+    d = SqtDeck()
+    assert _lib.host_lib().sqt_deck_read(str(tmp_path / "nope").encode(), C.byref(d)) == -1
+    assert _lib.host_lib().sqt_deck_write_template(str(tmp_path / "tmpl").encode()) == 0
+    txt = (tmp_path / "tmpl").read_text()
+    assert txt.startswith("kVal\t\t0.00000 \n") and txt.endswith("nCSkip\t\t0 \n----\n")
+
+
+def test_reference_sample_decks_parse():
+    """The reference's shipped decks (values quoted in SURVEY.md section 8d) in the NameList syntax."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "in.lmp2sqt.150")
+        with open(p, "w") as f:
+            f.write("NameList -- data\nkVal\t\t0.0981748 \ndeltaT\t\t0.0600000 \nmass\t\t1.00000 \nrVal\t\t0.200000 \n"
+                    "limitCorrAv\t14825 \nnCBuffer\t150 \nnCSpatial\t30 \nnCTime\t\t150 \n----\n")
+        d = Deck.read(p)
+        assert (d.kVal, d.deltaT, d.rVal, d.limitCorrAv, d.nCBuffer, d.nCSpatial, d.nCTime, d.nCSkip) == \
+               (0.0981748, 0.06, 0.2, 14825, 150, 30, 150, 0)
+
+
+def _read_all_frames(path):
+    h = _lib.host_lib()
+    fp = libc.fopen(path.encode(), b"r")
+    frames = []
+    hd = SqtFrameHeader()
+    while h.sqt_dump_read_header(fp, C.byref(hd)):
+        xyz = np.empty((3, hd.n_atoms))
+        assert h.sqt_dump_read_atoms(fp, C.byref(hd), xyz[0].ctypes.data, xyz[1].ctypes.data, xyz[2].ctypes.data)
+        frames.append((hd.timestep, hd.n_atoms, (hd.xlo, hd.xhi, hd.ylo, hd.yhi, hd.zlo, hd.zhi), xyz.copy()))
+    libc.fclose(fp)
+    return frames
+
+
+def test_dump_reader_matches_atof_bit_for_bit(tmp_path):
+    t = synth.make_trajectory(n_cells=3, n_atoms=77, n_frames=7, seed=5, box_jitter=0.02)
+    # make the numbers nasty: big unwrapped coordinates, negative values, many digits
+    t.positions[1] *= -1234.5
+    t.positions[2] += 9.87654321e5
+    p = tmp_path / "d.lammpstrj"
+    synth.write_text_dump(t, str(p))
+    frames = _read_all_frames(str(p))
+    assert len(frames) == 7
+    lines = p.read_text().split("\n")
+    per = 9 + 77
+    for f, (ts, n, box, xyz) in enumerate(frames):
+        assert ts == t.timesteps[f] and n == 77
+        ref = np.array([[float(v) for v in ln.split()[2:5]] for ln in lines[f * per + 9:(f + 1) * per]])  # Python float() == strtod
+        assert np.array_equal(xyz.T, ref)
+        assert box[1] == float(lines[f * per + 5].split()[1])
+
+
+def test_dump_reader_header_variants_and_garbage(tmp_path):
+    h = _lib.host_lib()
+    good = ("ITEM: TIMESTEP\n5\nITEM: NUMBER OF ATOMS\n2\nITEM: BOX BOUNDS pp pp ff\n0 1.5\n0 2\n-1 3e0\n"
+            "ITEM: ATOMS id type xu yu zu vx vy vz\n1 1 0.5 1e-3 -2.25 9 9 9\n2 1 1 2 3 9 9 9\n")
+    (tmp_path / "a").write_text(good + "ITEM: TIMESTEP\n6\nITEM: NUMBER OF ATOMS\n2\nITEM: BOX BOUNDS xx yy zz\n")
+    fr = _read_all_frames(str(tmp_path / "a"))
+    assert len(fr) == 1 and fr[0][2] == (0.0, 1.5, 0.0, 2.0, -1.0, 3.0)
+    assert np.array_equal(fr[0][3], [[0.5, 1.0], [1e-3, 2.0], [-2.25, 3.0]])
+    (tmp_path / "b").write_text("hello\n")
+    assert _read_all_frames(str(tmp_path / "b")) == []
+    (tmp_path / "c").write_text(good[:-12])  # truncated last atom line still parses what is there; truncated file -> stops
+    fp = libc.fopen(str(tmp_path / "c").encode(), b"r")
+    hd = SqtFrameHeader()
+    assert h.sqt_dump_read_header(fp, C.byref(hd)) == 1
+    libc.fclose(fp)
+
+
+def _results_from(raw: dict, S, T) -> Results:
+    r = Results(S, T)
+    m = {"avF_qq2": "avF", "StdDevF_qq2": "StdDevF", "avF_s_qq2": "avF_s", "StdDevF_s_qq2": "StdDevF_s",
+         "avF_d_qq2": "avF_d", "StdDevF_d_qq2": "StdDevF_d", "avDrTable": "avDrTable",
+         "rrMSDAv": "rrMSDAv", "rrMQDAv": "rrMQDAv", "rrMSDCMAv": "rrMSDCMAv"}
+    for k, v in m.items():
+        r.array(k)[...] = raw[v]
+    for k in ("countCorrAv", "limitCorrAv", "nPtls", "g_Vol", "kVal", "first_Vol", "first_limitCorrAv"):
+        setattr(r.c, k, raw[k])
+    return r
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_writers_reproduce_reference_files_byte_for_byte(name, tmp_path):
+    """PrintProcess: feed the raw sums (from the oracle, at the moment the reference printed) through
+    sqt_host_print_process and compare output.txt / output.binary / SSF / Dt / output.log with the reference's."""
+    c = load_case(name)
+    trajs = case_trajectories(name)
+    printed, raw, log = pyoracle.run_port(None, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0, limitCorrAv=c["limit"],
+                                          files=trajs, flags=c["flags"])
+    rp = printed["_raw_at_print"]
+    res = _results_from(rp, c["S"], c["T"])
+    deck = Deck.read(os.path.join(case_dir(name), "in.lmp2sqt"))
+    res.print_process(str(tmp_path), deck, c["flags"], date="GOLD")
+    g = case_dir(name)
+    assert filecmp.cmp(tmp_path / "output.binary", os.path.join(g, "output.binary"), shallow=False)
+    assert filecmp.cmp(tmp_path / "output.txt", os.path.join(g, "output.txt"), shallow=False)
+    assert filecmp.cmp(tmp_path / "output.log", os.path.join(g, "output.log"), shallow=False)
+    assert (tmp_path / "SSF000.info.GOLD").read_text() == open(os.path.join(g, "SSF000.info")).read()
+    assert (tmp_path / "Dt000.info.GOLD").read_text() == open(os.path.join(g, "Dt000.info")).read()
+    # the normalised arrays equal what the reference left in its globals
+    got = res.to_dict()
+    assert np.array_equal(got["avF_qq2"], printed["avF"]) and np.array_equal(got["rrMSDAv"], printed["rrMSDAv"])
+    assert np.array_equal(got["avDrTable"], printed["avDrTable"])
+    # second print in the same directory picks the next free index (lmp2sqt.c:886-902)
+    res2 = _results_from(rp, c["S"], c["T"])
+    res2.print_process(str(tmp_path), deck, c["flags"], date="GOLD")
+    assert (tmp_path / "Dt001.info.GOLD").exists() and (tmp_path / "SSF001.info.GOLD").exists()
+
+
+def test_factor_dr_matches_oracle():
+    t = synth.make_trajectory(n_cells=2, n_frames=30, seed=3)
+    S, T, B = 6, 5, 5
+    o = pyoracle.OraclePort(S, T, B, limitCorrAv=77)
+    o.begin_file()
+    for f in range(t.n_frames):
+        o.push_frame(t.positions[f], 0.0, t.box[f, 0, 1])
+    o.finish()
+    res = _results_from(o.printed_raw(), S, T)
+    fd = np.zeros(S)
+    _lib.host_lib().sqt_host_factor_dr(C.byref(res.c), 0.2, fd.ctypes.data)
+    assert np.array_equal(fd, o.factorDr())

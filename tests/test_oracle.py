@@ -1,0 +1,96 @@
+"""The oracle is only trustworthy if it is pinned: (1) against the committed golden vectors the UNMODIFIED
+reference produced (tests/golden/, runs anywhere), (2) against the reference itself, bit for bit, where
+oracle/_ref is available (this container; on the GPU box the prebuilt oracle/_ref travels with the repo)."""
+import os
+
+import numpy as np
+import pytest
+
+import pyoracle
+from golden_utils import CASES, case_dir, case_trajectories, load_case
+from lmp2sqt_b200 import synth
+
+N2 = pyoracle.NAMES2D
+N1 = pyoracle.NAMES1D
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_port_reproduces_reference_golden_arrays(name):
+    """Raw fp64 sums and normalised arrays read from the reference's globals: bit-identical."""
+    c = load_case(name)
+    trajs = case_trajectories(name)
+    printed, raw, log = pyoracle.run_port(None, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0,
+                                          limitCorrAv=10**9 - sum((t.n_frames - c["T"]) // (c["T"] // min(c["B"], c["T"])) for t in trajs),
+                                          files=trajs, flags=c["flags"], finish=False)
+    a = c["arrays"]
+    assert raw["countCorrAv"] == int(a["raw_countCorrAv"])
+    assert [l[0] for l in log] == list(a["count_log"])
+    for k in N2 + N1:
+        assert np.array_equal(raw[k], a["raw_" + k]), k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_port_reproduces_reference_output_binary(name):
+    """output.binary written by the reference CLI (exact fp64) vs the restatement driven like main()."""
+    c = load_case(name)
+    trajs = case_trajectories(name)
+    printed, raw, log = pyoracle.run_port(None, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0, limitCorrAv=c["limit"],
+                                          files=trajs, flags=c["flags"])
+    ob = pyoracle.parse_output_binary(os.path.join(case_dir(name), "output.binary"), c["S"], c["T"])
+    assert ob["magic"] == "##space-time corr" and ob["consumed"] == ob["size"]
+    assert np.array_equal(ob["full-density"], printed["avF"].T)
+    if "F" in c["flags"]:
+        assert np.array_equal(ob["self-density"], printed["avF_s"].T)
+        assert np.array_equal(ob["cross-density"], printed["avF_d"].T)
+    else:
+        assert ob["self-density"] is None and ob["cross-density"] is None
+    assert np.array_equal(ob["self-vanHove"], printed["avDrTable"].T)
+    assert ob["kVal"] == printed["kVal"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_port_matches_printed_msd_digits(name):
+    """MSD / MQD exist in the reference's files only at %8.4g (Dt*.info, lmp2sqt.c:1060): the restatement's
+    fp64 values must round to exactly those digits."""
+    c = load_case(name)
+    trajs = case_trajectories(name)
+    printed, _, _ = pyoracle.run_port(None, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0, limitCorrAv=c["limit"],
+                                      files=trajs, flags=c["flags"])
+    rows = [ln.split() for ln in open(os.path.join(case_dir(name), "Dt000.info")).read().strip().split("\n")[1:]]
+    for nt, r in enumerate(rows):
+        assert r[1] == ("%8.4g" % printed["rrMSDAv"][nt]).strip()
+        assert r[7] == ("%8.4g" % printed["rrMQDAv"][nt]).strip()
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("skip,flags", [(0, "Ft"), (2, "Ft"), (0, "ft"), (1, "t")])
+def test_port_bit_identical_to_live_reference(skip, flags):
+    """Fresh random trajectory (not a committed fixture), two input files, fluctuating box."""
+    t1 = synth.make_trajectory(n_cells=2, n_frames=47, box_jitter=0.01, seed=101 + skip)
+    t2 = synth.make_trajectory(n_cells=2, n_frames=31, box_jitter=0.01, seed=202 + skip)
+    S, T, B = 5, 10, 4
+    ref = pyoracle.run_reference([t1, t2], S, T, B, nCSkip=skip, limit=1000, flags=flags)
+    extra = sum((t.n_frames - T) // (T // B) for t in (t1, t2))
+    pr, raw, log = pyoracle.run_port(None, S, T, B, nCSkip=skip, limitCorrAv=1000 - extra, files=[t1, t2], flags=flags)
+    assert ref["raw"]["countCorrAv"] == raw["countCorrAv"] and ref["log"] == [l[0] for l in log]
+    for k in N2 + N1:
+        assert np.array_equal(ref["raw"][k], raw[k]), k
+        assert np.array_equal(ref["printed"][k], pr[k], equal_nan=True), k
+
+
+def test_known_answer_identities_on_the_oracle():
+    """KATs of SURVEY.md section 4 on the checker itself."""
+    S, T, B = 5, 6, 6
+    t = synth.static_trajectory(2, 20)
+    pr, raw, _ = pyoracle.run_port(t, S, T, B, limitCorrAv=10**6)
+    N, cnt = t.n_atoms, raw["countCorrAv"]
+    assert cnt == sum(max(0, (20 - (nb * T) // B) // T) for nb in range(B))
+    np.testing.assert_allclose(pr["avF_s"], 1.0, rtol=1e-12)
+    assert np.all(pr["rrMSDAv"] == 0)
+    np.testing.assert_allclose(pr["avF_d"], 2 * (pr["avF"] - pr["avF_s"]), atol=1e-12)
+    tr = synth.translating_trajectory(50, 40, d=(0.1, 0.0, 0.0), box_len=10.0)
+    pr, raw, _ = pyoracle.run_port(tr, 4, 5, 1, limitCorrAv=10**6)
+    k0 = 2 * np.pi / 10.0
+    m = np.arange(1, 5)[:, None]; tau = np.arange(5)[None, :]
+    np.testing.assert_allclose(pr["avF_s"], (np.cos(m * k0 * 0.1 * tau) + 2) / 3, rtol=1e-10)
+    np.testing.assert_allclose(pr["rrMSDAv"], 0.01 * tau[0] ** 2, rtol=1e-9)
