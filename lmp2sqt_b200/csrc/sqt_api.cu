@@ -47,6 +47,7 @@ struct sqt_handle {
 	double *d_ring;
 	int RP;
 	double *d_partial;
+	int *d_tile_ctr;
 	int *d_hist_cur, *d_bufHist;
 	double *d_bufFs, *d_bufF, *d_bufMSD, *d_bufMQD, *d_bufMSDCM;
 	double *d_rho0, *d_sumr0, *d_invL0, *d_rho_cur, *d_cblk;
@@ -150,7 +151,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->L = h->vol = h->first_vol = 0; h->kVal = p->kVal; h->first_limit = 0;
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
-	h->d_ring = nullptr; h->d_partial = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
+	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
 	h->d_avblk = h->d_latblk = nullptr;
@@ -229,7 +230,7 @@ extern "C" void sqt_destroy(sqt_handle *h)
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_ring[i]) cudaEventDestroy(h->ev_ring[i]);
 	}
-	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
+	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
 	cudaFree(h->d_bufFs); cudaFree(h->d_bufF); cudaFree(h->d_bufMSD); cudaFree(h->d_bufMQD); cudaFree(h->d_bufMSDCM);
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
@@ -303,14 +304,16 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 	cudaError_t e = cudaMalloc(&h->d_ring, ring_bytes);
 	if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin ring of %.2f GB does not fit on the device: %s", ring_bytes / 1e9, cudaGetErrorString(e));
 	CU(cudaMemsetAsync(h->d_ring, 0, ring_bytes, h->s_main));
-	const size_t part_bytes = sizeof(double) * (size_t)h->kc.blocks_p * h->kc.NV * h->kc.SPAD;
+	const size_t part_bytes = sizeof(double) * (size_t)h->kc.NWSG * h->kc.KW * h->kc.NV * (32 / h->kc.G);
 	CU(cudaMalloc(&h->d_partial, part_bytes));
 	CU(cudaMemsetAsync(h->d_partial, 0, part_bytes, h->s_main));
+	CU(cudaMalloc(&h->d_tile_ctr, sizeof(int) * h->kc.NWSG));
+	CU(cudaMemsetAsync(h->d_tile_ctr, 0, sizeof(int) * h->kc.NWSG, h->s_main));
 	snprintf(h->cfg, sizeof(h->cfg),
-	         "self_ring_kernel<C=%d,G=%d> grid=(%d,%d) block=%d regs=%d smem=%zuB occ=%d blocks/SM chunk=%d particles/block "
-	         "slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB",
-	         h->kc.C, h->kc.G, h->kc.blocks_p, h->kc.slot_groups, h->kc.WPB * 32, h->kc.regs, h->kc.smem, h->kc.occ,
-	         h->kc.chunk, h->B, SQT_NVIRT, ring_bytes / 1e9, part_bytes / 1e6);
+	         "self_ring_kernel<C=%d,G=%d> persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; %d slot groups x %d warps, "
+	         "%s tiles of %d particles (%d tiles); slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB",
+	         h->kc.C, h->kc.G, h->kc.blocks, h->kc.WPB * 32, h->kc.regs, h->kc.smem, h->kc.occ, h->kc.NWSG, h->kc.KW,
+	         h->kc.dynamic ? "dynamic" : "static", h->kc.tile, h->kc.ntiles, h->B, SQT_NVIRT, ring_bytes / 1e9, part_bytes / 1e6);
 	h->sized = true;
 	return SQT_OK;
 }
@@ -333,7 +336,8 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	RingArgs ra;
 	ra.cur = h->d_cur[slot]; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
 	ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = h->cur_pitch; ra.n_local = h->n_local;
-	ra.chunk = h->kc.chunk; ra.p = p; ra.T = T; ra.B = B; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
+	ra.tile = h->kc.tile; ra.ntiles = h->kc.ntiles; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
+	ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = B; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
 	ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
 	ra.varbox = varbox;
 	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -350,7 +354,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	const bool split = h->s_coll != h->s_main;
 	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0)); // previous frame's collective stage
 	ReduceArgs rr;
-	rr.partial = h->d_partial; rr.blocks_p = h->kc.blocks_p; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
+	rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
 	rr.p = p; rr.T = T; rr.B = B; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
 	rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.rho_cur = h->d_rho_cur; rr.invL0 = h->d_invL0; rr.invL = invL;
 	rc = sqt_launch_reduce(rr, h->s_main);

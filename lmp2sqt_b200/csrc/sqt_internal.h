@@ -11,13 +11,16 @@
 struct RingArgs {
 	const double *cur;        // current frame, SoA [3][cur_pitch]
 	double *ring;             // origin positions [n][3][RP]  (slot-minor: a warp reads 32 origins of one particle/axis contiguously)
-	double *partial;          // per-block partial sums [blocks_p][NV][SPAD]
+	double *partial;          // per-warp partial sums [slot group][k-th warp][NV][O]
+	int *tile_ctr;            // [NWSG] next particle tile per slot group (dynamic scheduling)
 	int *hist_cur;            // this frame's van Hove counts [B][nCS]   (zeroed by the reduce kernel)
 	const double *invL0;      // [B] 1/L of each buffer's origin frame
 	const long long *thr;     // [nCS+2] bit patterns of the exact bin thresholds (see host: build_thresholds)
 	long long cur_pitch;
 	int n_local;
-	int chunk;                // particles per block
+	int tile, ntiles;         // particles per tile, tiles in the shard
+	int NWSG, KW, total_warps; // slot groups, warps per slot group (upper bound), warps launched
+	int dynamic;              // 1: tiles handed out by atomic counter, 0: static round robin (bit-reproducible)
 	int p;                    // processed-frame index within the current input file
 	int T, B, nCS, RP;
 	int V0;                   // first virtual slot (B rounded up to even)
@@ -28,11 +31,11 @@ struct RingArgs {
 };
 
 struct KernelChoice {
-	int C, G;                 // chains per thread, lane groups per warp
+	int C, G, minb;           // chains per thread, lane groups per warp, launch-bounds variant
 	int WPB;                  // warps per block
-	int slot_groups;          // gridDim.y
-	int blocks_p;             // gridDim.x
-	int chunk;
+	int blocks;               // persistent 1-D grid
+	int NWSG, KW, total_warps;
+	int tile, ntiles, dynamic;
 	int SPAD, NV, CT, NSLOT, V0;
 	size_t smem;
 	int regs;                 // registers per thread reported by the runtime
@@ -46,7 +49,8 @@ int sqt_launch_ring(const KernelChoice &kc, const RingArgs &a, cudaStream_t st);
 
 struct ReduceArgs {
 	const double *partial;
-	int blocks_p, NV, SPAD, CT, V0, G;
+	int KW, NWSG, NV, SPAD, CT, V0, G;
+	int *tile_ctr;
 	int p, T, B, nCS;
 	int *hist_cur;            // [B][nCS] -> moved into bufHist, then zeroed
 	int *bufHist;             // [B][T][nCS]

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here without a GPU): python profiles/ncu_summary.py gpurun_out/prof.ncu-rep"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+        "smsp__average_warp_latency_per_inst_issued.ratio"]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    for r in data:
+        name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        print("== kernel:", name[:100])
+        for i, h in enumerate(hdr):
+            if h in KEYS:
+                print("  %-70s %s %s" % (h, r[i], units[i]))
+        st = [(float(r[i]), h[len(STALL):-len("_per_issue_active.ratio")]) for i, h in enumerate(hdr)
+              if h.startswith(STALL) and h.endswith("_per_issue_active.ratio")]
+        print("  stall reasons (warps stalled per issue-active cycle):")
+        for v, n in sorted(st, reverse=True)[:9]:
+            print("      %-28s %.3f" % (n, v))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
