@@ -1,0 +1,72 @@
+"""Drop-in check: the command-line driver (lmp2sqt_b200/bin/lmp2sqt_b200.out, C host code over the C-ABI) run
+exactly like the reference binary on the golden cases -- same flags, same deck, same text dumps -- must leave
+the same files behind: the rewritten deck byte for byte, output.binary / output.txt / SSF / Dt equal to the
+reference's files within the floating-point tolerance (values are printed at %8.4e / %8.4g, so text is
+compared numerically at the printed precision)."""
+import glob
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import pyoracle
+from golden_utils import CASES, case_dir, load_case, unpack_dumps
+from lmp2sqt_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _numbers(path):
+    out = []
+    for ln in open(path):
+        if ln.startswith("#"):
+            continue
+        out.append([float(x) for x in ln.split()])
+    return out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cli_is_a_drop_in_for_the_reference_binary(name, tmp_path):
+    c = load_case(name)
+    g = case_dir(name)
+    shutil.copy(os.path.join(g, "in.lmp2sqt"), tmp_path / "in.lmp2sqt")
+    dumps = unpack_dumps(name, str(tmp_path))
+    flags = {"Ft": ["-F", "-t"], "ft": ["-f", "-t"], "F": ["-F"], "t": ["-t"]}[c["flags"]]
+    r = subprocess.run([_lib.CLI_BIN, *flags, "-i", "in.lmp2sqt", *dumps], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # deck rewrite (UpdateNameList): byte-identical
+    assert (tmp_path / "in.lmp2sqt").read_bytes() == open(os.path.join(g, "in.lmp2sqt.after"), "rb").read()
+    # stdout banner lines of the flags
+    assert r.stdout == open(os.path.join(g, "stdout.txt")).read()
+    assert (tmp_path / "output.log").read_text() == open(os.path.join(g, "output.log")).read()
+    S, T = c["S"], c["T"]
+    got = pyoracle.parse_output_binary(str(tmp_path / "output.binary"), S, T)
+    ref = pyoracle.parse_output_binary(os.path.join(g, "output.binary"), S, T)
+    assert got["size"] == ref["size"] and got["magic"] == ref["magic"]
+    assert (got["kVal"], got["deltaT"], got["rVal"]) == (ref["kVal"], ref["deltaT"], ref["rVal"])
+    for key in ("full-density", "self-density", "cross-density"):
+        if ref[key] is None:
+            assert got[key] is None
+            continue
+        tol = 1e-6 * np.maximum(np.abs(ref[key]), 1e-3 * np.abs(ref[key][:1, :]))   # SURVEY.md 8a tolerance
+        assert np.all(np.abs(got[key] - ref[key]) <= tol), key
+    np.testing.assert_allclose(got["self-vanHove"], ref["self-vanHove"], rtol=1e-12)    # integer counts x factorDr
+    # text files, numerically at the printed precision
+    a, b = _numbers(tmp_path / "output.txt"), _numbers(os.path.join(g, "output.txt"))
+    assert [len(x) for x in a] == [len(x) for x in b]
+    for x, y in zip(a, b):
+        # sigma columns can be sqrt(tiny negative) = nan in both
+        np.testing.assert_allclose(x, y, rtol=2e-4, atol=1e-7, equal_nan=True)
+    for pat, gold in (("SSF000.info.*", "SSF000.info"), ("Dt000.info.*", "Dt000.info")):
+        f = glob.glob(str(tmp_path / pat))
+        assert len(f) == 1
+        x, y = np.array(_numbers(f[0])), np.array(_numbers(os.path.join(g, gold)))
+        assert x.shape == y.shape
+        np.testing.assert_allclose(x, y, rtol=2e-3, atol=1e-4, equal_nan=True)
+
+
+def test_cli_rejects_out_of_scope_flags(tmp_path):
+    r = subprocess.run([_lib.CLI_BIN, "-V", "x"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "outside the B200 hot path" in r.stderr
