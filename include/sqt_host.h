@@ -11,6 +11,7 @@
  *   UpdateNameList         lmp2sqt.c:2112-2125                sqt_deck_write
  *   ReadDumpForOnlyCheck   snapshot.c:25-165                  sqt_dump_read_header + sqt_dump_skip_atoms
  *   ReadDump               snapshot.c:166-382                 sqt_dump_read_header + sqt_dump_read_atoms (SoA)
+ *                                                             sqt_reader_* (mmap + threads, same semantics)
  *   Alloc_more tail        lmp2sqt.c:1987-2009 (factorDr)     sqt_host_factor_dr
  *   prePrintProcess        lmp2sqt.c:576-675                  sqt_host_normalise
  *   PrintProcess           lmp2sqt.c:338-367                  sqt_host_print_process
@@ -56,6 +57,16 @@ int sqt_dump_read_header(FILE *fp, sqt_frame_header *hd);
 /* Atom lines into SoA x[n], y[n], z[n] in file-line order (`id` is ignored, snapshot.c:357-368). 1 ok / 0 short file. */
 int sqt_dump_read_atoms(FILE *fp, const sqt_frame_header *hd, double *x, double *y, double *z);
 int sqt_dump_skip_atoms(FILE *fp, const sqt_frame_header *hd);
+
+/* High-rate variant of the same reader: memory-mapped file, atom block parsed by n_threads threads (0 = auto,
+ * SQT_READER_THREADS overrides) straight into the SoA staging buffer.  Same format rules and conversions. */
+typedef struct sqt_reader sqt_reader;
+sqt_reader *sqt_reader_open(const char *path, int n_threads);
+void sqt_reader_close(sqt_reader *r);
+void sqt_reader_rewind(sqt_reader *r);
+int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd);
+int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z);
+int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd);
 
 /* factorDr[nr], lmp2sqt.c:1987-2009, from what the engine recorded at the first processed frame. */
 void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr);

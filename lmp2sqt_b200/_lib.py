@@ -92,6 +92,12 @@ HOST_API = [
     ("sqt_dump_read_header", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
     ("sqt_dump_read_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("sqt_dump_skip_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
+    ("sqt_reader_open", C.c_void_p, [C.c_char_p, C.c_int]),
+    ("sqt_reader_close", None, [C.c_void_p]),
+    ("sqt_reader_rewind", None, [C.c_void_p]),
+    ("sqt_reader_next_header", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
+    ("sqt_reader_read_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sqt_reader_skip_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
     ("sqt_host_factor_dr", None, [C.POINTER(SqtResults), C.c_double, C.c_void_p]),
     ("sqt_host_normalise", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int]),
     ("sqt_host_print_process", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_char_p]),

@@ -89,12 +89,12 @@ int main(int argc, char **argv)
 	long *num_data = (long *)calloc(argc + 3, sizeof(long));
 	int runable = 0, full_n_snaps = 0;
 	for (int a = optind; a < argc; a++) {
-		FILE *fp = fopen(argv[a], "r");
-		if (!fp) { fprintf(stderr, "Can`t open file (%s)!!\n", argv[a]); continue; }
+		sqt_reader *rd = sqt_reader_open(argv[a], 0);
+		if (!rd) { fprintf(stderr, "Can`t open file (%s)!!\n", argv[a]); continue; }
 		int n_snap = 0;
 		sqt_frame_header hd;
-		while (sqt_dump_read_header(fp, &hd) && hd.n_atoms > 0 && sqt_dump_skip_atoms(fp, &hd)) n_snap++;
-		fclose(fp);
+		while (sqt_reader_next_header(rd, &hd) && hd.n_atoms > 0 && sqt_reader_skip_atoms(rd, &hd)) n_snap++;
+		sqt_reader_close(rd);
 		if (n_snap < 5) {
 			fprintf(stderr, "The # of snap is too small(<5) \n, or this file is not valid \nWe would  not use 	this file(%s)!!\n", argv[a]);
 		} else if (deck.nCBuffer < 1 || floor((n_snap - deck.nCTime) / (deck.nCTime / deck.nCBuffer)) < 1) {
@@ -123,11 +123,11 @@ int main(int argc, char **argv)
 	if (deck.nCBuffer > deck.nCTime) { fputs("Error nCBuffer> nCTime\n", stderr); exit(1); }
 
 	if (flag_d) { /* AmountAllocArray, lmp2sqt.c:1658-1820: report and stop */
-		FILE *fp = fopen(argv[optind], "r");
+		sqt_reader *rd = sqt_reader_open(argv[optind], 1);
 		sqt_frame_header hd;
 		long long n = 0;
-		if (fp && sqt_dump_read_header(fp, &hd)) n = hd.n_atoms;
-		if (fp) fclose(fp);
+		if (rd && sqt_reader_next_header(rd, &hd)) n = hd.n_atoms;
+		sqt_reader_close(rd);
 		int B = deck.nCBuffer < 1 ? 1 : deck.nCBuffer;
 		long long ring = 3LL * ((B + 15) / 16 * 16) * n * 8;
 		long long bufs = (long long)B * deck.nCTime * deck.nCSpatial * (8 + 8 + 4) + 14LL * deck.nCSpatial * deck.nCTime * 8;
@@ -147,10 +147,10 @@ int main(int argc, char **argv)
 	double kVal = deck.kVal;
 	for (int a = optind; a < argc; a++) {
 		if (!files_on[a]) continue;
-		FILE *fp = fopen(argv[a], "r");
+		sqt_reader *rd = sqt_reader_open(argv[a], 0);
 		sqt_begin_file(h); /* InitSpacetimeCorr, :282 */
 		sqt_frame_header hd;
-		if (sqt_dump_read_header(fp, &hd)) { /* Init_reciprocal_space, :2171-2202 (message only: kVal is reset per frame) */
+		if (sqt_reader_next_header(rd, &hd)) { /* Init_reciprocal_space, :2171-2202 (message only: kVal is reset per frame) */
 			double L0 = hd.xhi - hd.xlo;
 			int n_mul = (int)round(kVal / (2. * M_PI / L0));
 			if (n_mul <= 0) n_mul = 1;
@@ -158,13 +158,13 @@ int main(int argc, char **argv)
 			fprintf(stderr, "Update for input dk param: %f -> %f \n", kVal, new_dk);
 			kVal = new_dk;
 		}
-		rewind(fp);
+		sqt_reader_rewind(rd);
 		fprintf(stderr, "FULL_SNAPS = %5d\n", full_n_snaps);
 		for (long ns = 0; ns < num_data[a]; ns++) {
-			if (!sqt_dump_read_header(fp, &hd)) break;
+			if (!sqt_reader_next_header(rd, &hd)) break;
 			double *stage = sqt_stage_acquire(h, hd.n_atoms);
 			if (!stage) die_engine(h, "sqt_stage_acquire", -1);
-			if (!sqt_dump_read_atoms(fp, &hd, stage, stage + hd.n_atoms, stage + 2 * (size_t)hd.n_atoms)) break;
+			if (!sqt_reader_read_atoms(rd, &hd, stage, stage + hd.n_atoms, stage + 2 * (size_t)hd.n_atoms)) break;
 			rc = sqt_push_frame(h, stage, hd.n_atoms, hd.n_atoms, hd.xlo, hd.xhi); /* EvalSpacetimeCorr, :300 */
 			if (rc < 0) die_engine(h, "sqt_push_frame", rc);
 			if (rc == SQT_FLUSH) { /* PrintProcess from AccumSpacetimeCorr, :438-440 */
@@ -181,7 +181,7 @@ int main(int argc, char **argv)
 				fflush(stderr);
 			}
 		}
-		fclose(fp);
+		sqt_reader_close(rd);
 		fprintf(stderr, "\nEnd : file : %s\n", argv[a]);
 	}
 	rc = sqt_finish(h, &res);

@@ -183,3 +183,63 @@ def test_factor_dr_matches_oracle():
     fd = np.zeros(S)
     _lib.host_lib().sqt_host_factor_dr(C.byref(res.c), 0.2, fd.ctypes.data)
     assert np.array_equal(fd, o.factorDr())
+
+
+def _read_all_frames_mmap(path, threads):
+    h = _lib.host_lib()
+    r = h.sqt_reader_open(path.encode(), threads)
+    assert r
+    frames = []
+    hd = SqtFrameHeader()
+    while h.sqt_reader_next_header(r, C.byref(hd)):
+        xyz = np.empty((3, hd.n_atoms))
+        if not h.sqt_reader_read_atoms(r, C.byref(hd), xyz[0].ctypes.data, xyz[1].ctypes.data, xyz[2].ctypes.data):
+            break
+        frames.append((hd.timestep, hd.n_atoms, (hd.xlo, hd.xhi, hd.ylo, hd.yhi, hd.zlo, hd.zhi), xyz.copy()))
+    h.sqt_reader_close(r)
+    return frames
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_mmap_reader_equals_stream_reader(tmp_path, threads):
+    """The threaded, memory-mapped reader must return exactly what the line-by-line reader returns."""
+    t = synth.make_trajectory(n_cells=9, n_atoms=2777, n_frames=5, seed=8, box_jitter=0.02)   # > 2048 atoms: several threads
+    t.positions[1] *= -321.5
+    t.positions[3] += 1.234567e6
+    p = tmp_path / "d.lammpstrj"
+    synth.write_text_dump(t, str(p))
+    # exponent notation and a Windows line ending exercise the strtod fallback
+    txt = p.read_text().split("\n")
+    txt[9] = "1 1 1.5e+01 -2.5E-3 3.25e0"
+    txt[10] = txt[10] + "\r"
+    p.write_text("\n".join(txt))
+    a, b = _read_all_frames(str(p)), _read_all_frames_mmap(str(p), threads)
+    assert len(a) == len(b) == 5
+    for (ts1, n1, box1, x1), (ts2, n2, box2, x2) in zip(a, b):
+        assert (ts1, n1, box1) == (ts2, n2, box2)
+        assert np.array_equal(x1, x2)
+    assert a[0][3][0, 0] == 15.0 and a[0][3][1, 0] == -2.5e-3
+    # count pass (ReadDumpForOnlyCheck analogue)
+    h = _lib.host_lib()
+    r = h.sqt_reader_open(str(p).encode(), 1)
+    hd = SqtFrameHeader()
+    n = 0
+    while h.sqt_reader_next_header(r, C.byref(hd)) and h.sqt_reader_skip_atoms(r, C.byref(hd)):
+        n += 1
+    h.sqt_reader_rewind(r)
+    assert h.sqt_reader_next_header(r, C.byref(hd)) == 1 and hd.timestep == 0
+    h.sqt_reader_close(r)
+    assert n == 5
+
+
+def test_mmap_reader_truncated_and_missing(tmp_path):
+    h = _lib.host_lib()
+    assert not h.sqt_reader_open(str(tmp_path / "nope").encode(), 1)
+    t = synth.make_trajectory(n_cells=2, n_frames=3, seed=1)
+    p = tmp_path / "d"
+    synth.write_text_dump(t, str(p))
+    data = p.read_bytes()
+    (tmp_path / "cut").write_bytes(data[: len(data) - 200])      # last frame loses atom lines
+    assert len(_read_all_frames_mmap(str(tmp_path / "cut"), 2)) == 2
+    (tmp_path / "empty").write_bytes(b"")
+    assert _read_all_frames_mmap(str(tmp_path / "empty"), 2) == []
