@@ -70,3 +70,32 @@ def test_cli_is_a_drop_in_for_the_reference_binary(name, tmp_path):
 def test_cli_rejects_out_of_scope_flags(tmp_path):
     r = subprocess.run([_lib.CLI_BIN, "-V", "x"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0 and "outside the B200 hot path" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(pyoracle.REF_ANALYSIS_BIN), reason="oracle/_ref/analysis_binary_ref.out not built")
+@pytest.mark.parametrize("name", ["g2_final_print", "g5_ring30"])
+def test_reference_analysis_binary_consumes_our_output(name, tmp_path):
+    """the reference's own post-processor (analysis_binary.c, unmodified, built into
+    oracle/_ref) run on OUR output.binary gives the same Fqt / Fqt_scaled / GammaQt / Dqt / D0Hqt files as when it
+    is run on the reference's output.binary."""
+    c = load_case(name)
+    g = case_dir(name)
+    ours, theirs = tmp_path / "ours", tmp_path / "theirs"
+    ours.mkdir(); theirs.mkdir()
+    shutil.copy(os.path.join(g, "in.lmp2sqt"), ours / "in.lmp2sqt")
+    dumps = unpack_dumps(name, str(ours))
+    r = subprocess.run([_lib.CLI_BIN, "-F", "-t", "-i", "in.lmp2sqt", *dumps], cwd=ours, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    shutil.copy(os.path.join(g, "output.binary"), theirs / "output.binary")
+    shutil.copy(os.path.join(g, "in.lmp2sqt.after"), theirs / "in.lmp2sqt")   # analysis_binary reads ./in.lmp2sqt (:184)
+    for d in (ours, theirs):
+        rr = subprocess.run([pyoracle.REF_ANALYSIS_BIN, "output.binary"], cwd=d, capture_output=True, text=True)
+        assert rr.returncode == 0
+    files = sorted(f for f in os.listdir(theirs) if f.endswith(".info") or f.endswith(".out"))
+    assert len(files) >= 20
+    for f in files:
+        a, b = _numbers(ours / f), _numbers(theirs / f)
+        assert [len(x) for x in a] == [len(x) for x in b], f
+        derived = f.startswith(("GammaQt", "Dqt", "D0Hqt", "Fqt1"))     # finite differences of F and ln F amplify rounding
+        for x, y in zip(a, b):
+            np.testing.assert_allclose(x, y, rtol=1e-4 if derived else 2e-6, atol=1e-6 if derived else 1e-9, equal_nan=True, err_msg=f)
