@@ -137,3 +137,95 @@ def test_cubic_lattice_structure_factor():
     Sq = g["avF_qq2"][:, 0] / (3.0 * N * cnt)
     want = np.array([N if (m % n == 0) else 0.0 for m in range(1, S + 1)])
     np.testing.assert_allclose(Sq, want, atol=1e-9 * N)
+
+
+@pytest.mark.parametrize("S", [200, 700])
+def test_very_large_nCSpatial(S):
+    """Beyond the BASELINE shapes: 8 and 16 lane groups per warp."""
+    traj = synth.make_trajectory(n_cells=2, n_atoms=21, n_frames=14, seed=6)
+    got, raw, eng, _ = _run_both([traj], S, 4, 4)
+    check_raw_sums(got, raw, traj.n_atoms, label="S%d " % S)
+
+
+@pytest.mark.parametrize("T,B", [(5, 1), (7, 7), (6, 99), (450 // 30, 450 // 30)])
+def test_ring_shapes(T, B):
+    """One buffer, B == T, nCBuffer > nCTime (clipped like GetNameList does, lmp2sqt.c:2105)."""
+    traj = synth.make_trajectory(n_cells=2, n_frames=40, seed=12)
+    got, raw, eng, _ = _run_both([traj], 3, T, B)
+    check_raw_sums(got, raw, traj.n_atoms, label="T%d B%d " % (T, B))
+
+
+def test_device_and_pinned_host_frames_equal_staged_frames():
+    """The three ingest paths (engine staging, caller's pinned memory, device-resident frame) give identical sums."""
+    import ctypes as C
+    import torch
+    from lmp2sqt_b200 import SpacetimeCorr
+    traj = synth.make_trajectory(n_cells=3, n_frames=30, seed=21)
+    n = traj.n_atoms
+    deck = Deck(limitCorrAv=BIG, nCBuffer=4, nCSpatial=9, nCTime=8)
+    outs = []
+    for mode in ("staged", "pinned", "device", "pageable"):
+        eng = SpacetimeCorr(deck)
+        eng.InitSpacetimeCorr()
+        keep = []
+        for f in range(traj.n_frames):
+            soa = np.ascontiguousarray(traj.positions[f].T)
+            L = traj.box[f, 0, 1]
+            if mode == "staged":
+                eng.EvalSpacetimeCorr(traj.positions[f], 0.0, L)
+            elif mode == "pageable":
+                eng._check(eng.lib.sqt_push_frame(eng.h, soa.ctypes.data, n, n, 0.0, float(L)), "push")
+            elif mode == "pinned":
+                t = torch.from_numpy(soa).pin_memory()
+                keep.append(t)
+                eng._check(eng.lib.sqt_push_frame(eng.h, C.c_void_p(t.data_ptr()), n, n, 0.0, float(L)), "push")
+            else:
+                t = torch.from_numpy(soa).cuda()
+                torch.cuda.synchronize()
+                keep.append(t)
+                eng.push_device(t.data_ptr(), n, n, 0.0, L)
+        outs.append(eng.fetch().to_dict())
+        eng.close()
+    for o in outs[1:]:
+        for k in ("avF_qq2", "avF_s_qq2", "avF_d_qq2", "rrMSDAv", "rrMQDAv", "rrMSDCMAv", "avDrTable"):
+            np.testing.assert_allclose(o[k], outs[0][k], rtol=1e-12, atol=1e-12)
+        assert o["countCorrAv"] == outs[0]["countCorrAv"]
+
+
+def test_synth_source_is_shard_independent():
+    """The on-device frame source generates the same atoms whatever slice a rank owns (counter-based RNG)."""
+    from lmp2sqt_b200 import SynthSource
+    full = SynthSource(3, 0, 108)
+    a, b = SynthSource(3, 0, 40), SynthSource(3, 40, 68)
+    for _ in range(3):
+        full.next(); a.next(); b.next()
+        f = full.to_host()
+        assert np.array_equal(f[:, :40], a.to_host()) and np.array_equal(f[:, 40:], b.to_host())
+    assert abs(full.L - (108 / 0.8442) ** (1 / 3)) < 1e-12
+    step = full.to_host().copy()
+    full.next()
+    d = full.to_host() - step
+    assert 0.05 < d.std() < 0.11          # sigma_step = 0.077 per axis per frame
+
+
+def test_atom_count_change_is_an_error():
+    from lmp2sqt_b200 import SpacetimeCorr, SqtError
+    eng = SpacetimeCorr(Deck(limitCorrAv=BIG, nCBuffer=2, nCSpatial=3, nCTime=4))
+    eng.InitSpacetimeCorr()
+    eng.EvalSpacetimeCorr(np.random.rand(10, 3), 0.0, 5.0)
+    with pytest.raises(SqtError, match="atom count changed"):
+        eng.EvalSpacetimeCorr(np.random.rand(11, 3), 0.0, 5.0)
+    with pytest.raises(SqtError, match="xhi must exceed xlo"):
+        eng.EvalSpacetimeCorr(np.random.rand(10, 3), 1.0, 1.0)
+    eng.close()
+
+
+def test_deterministic_mode_is_bit_reproducible(monkeypatch):
+    monkeypatch.setenv("SQT_DETERMINISTIC", "1")
+    traj = synth.make_trajectory(n_cells=4, n_frames=20, seed=33)
+    deck = Deck(limitCorrAv=BIG, nCBuffer=3, nCSpatial=12, nCTime=6)
+    a, _ = run_trajectories([traj], deck)
+    b, _ = run_trajectories([traj], deck)
+    a, b = a.to_dict(), b.to_dict()
+    for k in ("avF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "rrMSDAv", "rrMQDAv"):
+        assert np.array_equal(a[k], b[k]), k
