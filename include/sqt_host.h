@@ -60,8 +60,14 @@ int sqt_dump_skip_atoms(FILE *fp, const sqt_frame_header *hd);
 
 /* High-rate variant of the same reader: memory-mapped file, atom block parsed by n_threads threads (0 = auto,
  * SQT_READER_THREADS overrides) straight into the SoA staging buffer.  Same format rules and conversions. */
+/* The same reader also accepts the raw binary frame file (an extension; the reference reads text only):
+ *   "SQTRAW01", then per frame: int64 timestep, int64 n_atoms, f64 xlo xhi ylo yhi zlo zhi, f64 x[n], y[n], z[n]
+ * (little endian, atoms in dump order).  It is recognised by its magic; sqt_raw_append_frame writes one frame. */
 typedef struct sqt_reader sqt_reader;
 sqt_reader *sqt_reader_open(const char *path, int n_threads);
+int sqt_reader_is_raw(const sqt_reader *r);
+int sqt_raw_append_frame(const char *path, int create, long long timestep, long long n_atoms, const double box[6],
+                         const double *x, const double *y, const double *z);
 void sqt_reader_close(sqt_reader *r);
 void sqt_reader_rewind(sqt_reader *r);
 int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd);

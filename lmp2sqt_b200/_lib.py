@@ -94,6 +94,8 @@ HOST_API = [
     ("sqt_dump_skip_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
     ("sqt_reader_open", C.c_void_p, [C.c_char_p, C.c_int]),
     ("sqt_reader_close", None, [C.c_void_p]),
+    ("sqt_reader_is_raw", C.c_int, [C.c_void_p]),
+    ("sqt_raw_append_frame", C.c_int, [C.c_char_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("sqt_reader_rewind", None, [C.c_void_p]),
     ("sqt_reader_next_header", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
     ("sqt_reader_read_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -27,7 +27,15 @@ struct sqt_reader {
 	const char *base;
 	size_t size, pos;
 	int fd, n_threads;
+	int raw;          /* 1: SQTRAW01 binary frame file (see sqt_host.h), 0: LAMMPS text dump */
 };
+
+/* Raw binary frame file (extension, SURVEY.md section 8f.1 "raw f64[3][N] frame file"):
+ *   file   := "SQTRAW01" frame*
+ *   frame  := int64 timestep, int64 n_atoms, f64 xlo xhi ylo yhi zlo zhi, f64 x[n], f64 y[n], f64 z[n]
+ * little endian, no padding.  Atom order is the dump order, exactly what the text path would deliver. */
+#define RAW_MAGIC "SQTRAW01"
+#define RAW_HDR (8 + 8 + 6 * 8)
 
 static int starts_with(const char *p, const char *end, const char *prefix)
 {
@@ -135,6 +143,7 @@ sqt_reader *sqt_reader_open(const char *path, int n_threads)
 	n_threads = 1;
 #endif
 	r->n_threads = n_threads < 1 ? 1 : n_threads;
+	if (r->size >= 8 && memcmp(r->base, RAW_MAGIC, 8) == 0) { r->raw = 1; r->pos = 8; }
 	return r;
 }
 
@@ -146,13 +155,25 @@ void sqt_reader_close(sqt_reader *r)
 	free(r);
 }
 
-void sqt_reader_rewind(sqt_reader *r) { if (r) r->pos = 0; }
+void sqt_reader_rewind(sqt_reader *r) { if (r) r->pos = r->raw ? 8 : 0; }
+int sqt_reader_is_raw(const sqt_reader *r) { return r ? r->raw : 0; }
 
 int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd)
 {
 	const char *p, *e;
 	size_t pos = r->pos;
 	memset(hd, 0, sizeof(*hd));
+	if (r->raw) {
+		if (r->size - pos < RAW_HDR) return 0;
+		long long ts, n;
+		double box[6];
+		memcpy(&ts, r->base + pos, 8); memcpy(&n, r->base + pos + 8, 8); memcpy(box, r->base + pos + 16, 48);
+		if (n <= 0 || n > 2147483647LL || (r->size - pos - RAW_HDR) / 24 < (size_t)n) return 0;
+		hd->timestep = (long)ts; hd->n_atoms = (int)n; hd->pbcType = 7;
+		hd->xlo = box[0]; hd->xhi = box[1]; hd->ylo = box[2]; hd->yhi = box[3]; hd->zlo = box[4]; hd->zhi = box[5];
+		r->pos = pos + RAW_HDR;
+		return 1;
+	}
 	if (!take_line(r, &pos, &p, &e) || !starts_with(p, e, "ITEM: TIMESTEP")) return 0;
 	if (!take_line(r, &pos, &p, &e)) return 0;
 	hd->timestep = parse_long(p, e);
@@ -203,6 +224,7 @@ int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd)
 {
 	size_t endp, dummy;
 	if (hd->n_atoms <= 0) return 1;
+	if (r->raw) { r->pos += (size_t)hd->n_atoms * 24; return 1; }
 	if (!index_lines(r, hd->n_atoms, hd->n_atoms, &dummy, 1, &endp)) { r->pos = r->size; return 0; }
 	r->pos = endp;
 	return 1;
@@ -212,6 +234,12 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 {
 	const int n = hd->n_atoms;
 	if (n <= 0) return 1;
+	if (r->raw) { /* already SoA: three straight copies into the staging buffer */
+		const char *src = r->base + r->pos;
+		memcpy(x, src, (size_t)n * 8); memcpy(y, src + (size_t)n * 8, (size_t)n * 8); memcpy(z, src + (size_t)n * 16, (size_t)n * 8);
+		r->pos += (size_t)n * 24;
+		return 1;
+	}
 	int T = r->n_threads;
 	if (T > n / 2048 + 1) T = n / 2048 + 1; /* threads only pay off on big blocks */
 	const int step = (n + T - 1) / T;
@@ -239,4 +267,21 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 	}
 	r->pos = endp;
 	return bad ? 0 : 1;
+}
+
+int sqt_raw_append_frame(const char *path, int create, long long timestep, long long n_atoms, const double box[6],
+                         const double *x, const double *y, const double *z)
+{
+	FILE *fp = fopen(path, create ? "wb" : "ab");
+	if (!fp) return -1;
+	int ok = 1;
+	if (create) ok &= fwrite(RAW_MAGIC, 1, 8, fp) == 8;
+	ok &= fwrite(&timestep, 8, 1, fp) == 1;
+	ok &= fwrite(&n_atoms, 8, 1, fp) == 1;
+	ok &= fwrite(box, 8, 6, fp) == 6;
+	ok &= fwrite(x, 8, (size_t)n_atoms, fp) == (size_t)n_atoms;
+	ok &= fwrite(y, 8, (size_t)n_atoms, fp) == (size_t)n_atoms;
+	ok &= fwrite(z, 8, (size_t)n_atoms, fp) == (size_t)n_atoms;
+	fclose(fp);
+	return ok ? 0 : -1;
 }

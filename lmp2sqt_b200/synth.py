@@ -179,3 +179,20 @@ def write_deck(path, kVal=0.0981748, deltaT=0.06, mass=1.0, rVal=0.2, limitCorrA
         if nCSkip is not None:
             f.write("nCSkip\t\t%d \n" % nCSkip)
         f.write("----\n")
+
+
+def write_raw_dump(traj: Trajectory, path: str, frames: slice | None = None) -> None:
+    """Write ``traj`` as a raw binary frame file (SQTRAW01, include/sqt_host.h) -- the high-rate alternative to text."""
+    import ctypes as C
+    from . import _lib
+    h = _lib.host_lib()
+    rng = range(traj.n_frames)[frames] if frames is not None else range(traj.n_frames)
+    first = True
+    for fi in rng:
+        soa = np.ascontiguousarray(traj.positions[fi].T, dtype=np.float64)
+        box = np.ascontiguousarray(traj.box[fi].reshape(6), dtype=np.float64)
+        rc = h.sqt_raw_append_frame(os.fsencode(path), int(first), int(traj.timesteps[fi]), traj.n_atoms, box.ctypes.data,
+                                    soa[0].ctypes.data, soa[1].ctypes.data, soa[2].ctypes.data)
+        if rc:
+            raise OSError("sqt_raw_append_frame failed for %s" % path)
+        first = False

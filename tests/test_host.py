@@ -243,3 +243,28 @@ def test_mmap_reader_truncated_and_missing(tmp_path):
     assert len(_read_all_frames_mmap(str(tmp_path / "cut"), 2)) == 2
     (tmp_path / "empty").write_bytes(b"")
     assert _read_all_frames_mmap(str(tmp_path / "empty"), 2) == []
+
+
+def test_raw_binary_frame_file_equals_text_dump(tmp_path):
+    """Extension pinned by self-consistency: the raw binary frame file carries exactly the coordinates the text dump
+    carries (those are rounded to %.6f by synth), and both come out of the same reader interface identically."""
+    t = synth.make_trajectory(n_cells=3, n_atoms=77, n_frames=6, seed=4, box_jitter=0.01)
+    synth.write_text_dump(t, str(tmp_path / "d.lammpstrj"))
+    synth.write_raw_dump(t, str(tmp_path / "d.sqtraw"))
+    a = _read_all_frames_mmap(str(tmp_path / "d.lammpstrj"), 2)
+    b = _read_all_frames_mmap(str(tmp_path / "d.sqtraw"), 2)
+    assert len(a) == len(b) == 6
+    for (ts1, n1, box1, x1), (ts2, n2, box2, x2) in zip(a, b):
+        assert (ts1, n1, box1) == (ts2, n2, box2) and np.array_equal(x1, x2)
+    h = _lib.host_lib()
+    r = h.sqt_reader_open(str(tmp_path / "d.sqtraw").encode(), 1)
+    assert h.sqt_reader_is_raw(r) == 1
+    hd = SqtFrameHeader()
+    n = 0
+    while h.sqt_reader_next_header(r, C.byref(hd)) and h.sqt_reader_skip_atoms(r, C.byref(hd)):
+        n += 1
+    h.sqt_reader_close(r)
+    assert n == 6
+    data = (tmp_path / "d.sqtraw").read_bytes()
+    (tmp_path / "cut.sqtraw").write_bytes(data[:-100])          # truncated last frame is not delivered
+    assert len(_read_all_frames_mmap(str(tmp_path / "cut.sqtraw"), 1)) == 5
