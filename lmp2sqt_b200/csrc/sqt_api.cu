@@ -57,6 +57,9 @@ struct sqt_handle {
 	bool latched;
 	int latched_count, latched_limit;
 	KernelChoice kc;
+	MmaChoice mc;             // blocked-Chebyshev / DMMA path for the real slots (large nCSpatial)
+	double *d_mma_partial;
+	int *d_mma_ctr;
 	cudaStream_t s_main, s_copy, s_coll;
 	cudaEvent_t ev_red, ev_coll, ev_t0, ev_t1;
 	bool coll_pending;
@@ -151,7 +154,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->L = h->vol = h->first_vol = 0; h->kVal = p->kVal; h->first_limit = 0;
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
-	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
+	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
 	h->d_avblk = h->d_latblk = nullptr;
@@ -230,7 +233,7 @@ extern "C" void sqt_destroy(sqt_handle *h)
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_ring[i]) cudaEventDestroy(h->ev_ring[i]);
 	}
-	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
+	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
 	cudaFree(h->d_bufFs); cudaFree(h->d_bufF); cudaFree(h->d_bufMSD); cudaFree(h->d_bufMQD); cudaFree(h->d_bufMSDCM);
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
@@ -297,7 +300,10 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 	h->nPtls = n_total;
 	h->cur_pitch = ((long long)n_local + 31) & ~31LL;
 	for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_cur[i], sizeof(double) * 3 * h->cur_pitch));
-	int rc = sqt_pick_kernel(h->S, h->B, n_local, h->n_sm, &h->kc);
+	int rc = sqt_pick_mma(h->S, h->B, n_local, h->n_sm, &h->mc);
+	if (rc != 0) return fail(h, SQT_ERR_CUDA, "mma kernel selection failed (rc=%d)", rc);
+	// with the mma path on, the classic kernel serves only the six virtual rho(k) slots (B = 0 for it)
+	rc = sqt_pick_kernel(h->S, h->mc.on ? 0 : h->B, n_local, h->n_sm, &h->kc);
 	if (rc != 0) return fail(h, SQT_ERR_CUDA, "no ring-kernel variant for nCSpatial=%d (rc=%d)", h->S, rc);
 	h->RP = (h->B + 15) & ~15; // 128-byte rows: a warp's 32 origins of one particle/axis are contiguous
 	const size_t ring_bytes = sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
@@ -309,11 +315,26 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 	CU(cudaMemsetAsync(h->d_partial, 0, part_bytes, h->s_main));
 	CU(cudaMalloc(&h->d_tile_ctr, sizeof(int) * h->kc.NWSG));
 	CU(cudaMemsetAsync(h->d_tile_ctr, 0, sizeof(int) * h->kc.NWSG, h->s_main));
-	snprintf(h->cfg, sizeof(h->cfg),
+	size_t mma_bytes = 0;
+	if (h->mc.on) {
+		mma_bytes = sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * h->mc.NT * 64;
+		CU(cudaMalloc(&h->d_mma_partial, mma_bytes));
+		CU(cudaMemsetAsync(h->d_mma_partial, 0, mma_bytes, h->s_main));
+		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * h->mc.NWSG));
+		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * h->mc.NWSG, h->s_main));
+	}
+	int off = 0;
+	if (h->mc.on)
+		off = snprintf(h->cfg, sizeof(h->cfg),
+		               "self_ring_mma_kernel<NT=%d,SPW=%d> (blocked Chebyshev S=%d on DMMA) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
+		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
+		               h->mc.NT, h->mc.SPW, h->mc.S, h->mc.blocks, h->mc.WPB * 32, h->mc.regs, h->mc.smem, h->mc.occ, h->mc.NWSG, h->mc.KW,
+		               h->mc.dynamic ? "dynamic" : "static", h->mc.tile);
+	snprintf(h->cfg + off, sizeof(h->cfg) - off,
 	         "self_ring_kernel<C=%d,G=%d> persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; %d slot groups x %d warps, "
 	         "%s tiles of %d particles (%d tiles); slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB",
 	         h->kc.C, h->kc.G, h->kc.blocks, h->kc.WPB * 32, h->kc.regs, h->kc.smem, h->kc.occ, h->kc.NWSG, h->kc.KW,
-	         h->kc.dynamic ? "dynamic" : "static", h->kc.tile, h->kc.ntiles, h->B, SQT_NVIRT, ring_bytes / 1e9, part_bytes / 1e6);
+	         h->kc.dynamic ? "dynamic" : "static", h->kc.tile, h->kc.ntiles, h->B, SQT_NVIRT, ring_bytes / 1e9, (part_bytes + mma_bytes) / 1e6);
 	h->sized = true;
 	return SQT_OK;
 }
@@ -333,11 +354,12 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	for (int nb = 0; nb < B; ++nb)
 		if (h->count[nb] > 0 && h->h_invL0[nb] != invL) { varbox = 1; break; }
 
+	const int Bc = h->mc.on ? 0 : B; // slots the classic kernel treats as real
 	RingArgs ra;
 	ra.cur = h->d_cur[slot]; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
 	ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = h->cur_pitch; ra.n_local = h->n_local;
 	ra.tile = h->kc.tile; ra.ntiles = h->kc.ntiles; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
-	ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = B; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
+	ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = Bc; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
 	ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
 	ra.varbox = varbox;
 	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -345,7 +367,19 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		CU(cudaEventCreate(&pe0)); CU(cudaEventCreate(&pe1));
 		CU(cudaEventRecord(pe0, h->s_main));
 	}
-	int rc = sqt_launch_ring(h->kc, ra, h->s_main);
+	int rc;
+	if (h->mc.on) {
+		MmaArgs ma;
+		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local; ma.tile = h->mc.tile;
+		ma.ntiles = h->mc.ntiles; ma.NWSG = h->mc.NWSG; ma.KW = h->mc.KW; ma.total_warps = h->mc.total_warps; ma.dynamic = h->mc.dynamic;
+		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->RP; ma.S = h->mc.S; ma.NT = h->mc.NT; ma.invL = invL;
+		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+		rc = sqt_launch_mma(h->mc, ma, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+	}
+	rc = sqt_launch_ring(h->kc, ra, h->s_main);
 	if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 	if (h->prof) { CU(cudaEventRecord(pe1, h->s_main)); h->prof_ev.push_back(pe0); h->prof_ev.push_back(pe1); }
 	CU(cudaEventRecord(h->ev_ring[slot], h->s_main));
@@ -355,8 +389,17 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0)); // previous frame's collective stage
 	ReduceArgs rr;
 	rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
-	rr.p = p; rr.T = T; rr.B = B; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
+	rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
 	rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.rho_cur = h->d_rho_cur; rr.invL0 = h->d_invL0; rr.invL = invL;
+	if (h->mc.on) {
+		MmaReduceArgs mr;
+		mr.partial = h->d_mma_partial; mr.KW = h->mc.KW; mr.NWSG = h->mc.NWSG; mr.S = h->mc.S; mr.NT = h->mc.NT; mr.SPW = h->mc.SPW;
+		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
+		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
+		rc = sqt_launch_mma_reduce(mr, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "mma_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+	}
 	rc = sqt_launch_reduce(rr, h->s_main);
 	if (rc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 	h->launches++;

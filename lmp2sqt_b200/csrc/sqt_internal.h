@@ -42,6 +42,43 @@ struct KernelChoice {
 	int occ;                  // resident blocks per SM
 };
 
+// ---- blocked-Chebyshev / FP64 tensor-core variant of the ring kernel (large nCSpatial) ---------------
+// m = S*b + r (b < 8, r < S):  sum_n T_m = 2 G[b][r] - sum_n T_{|S b - r|},  G[b][r] = sum_n T_{S b}(c_n) T_r(c_n)
+// G is an (8 x 3N)(3N x 8 NT) product per origin slot, accumulated by mma.sync m8n8k4 f64.
+struct MmaArgs {
+	const double *cur;        // current frame, SoA [3][cur_pitch]
+	double *ring;             // origin positions [n][3][RP]
+	double *partial;          // per-warp G fragments [slot group][k-th warp][SPW][NT][32 lanes][2]
+	int *tile_ctr;            // [NWSG]
+	int *hist_cur;            // [B][nCS]
+	const double *invL0;      // [B]
+	const long long *thr;     // [nCS+2]
+	long long cur_pitch;
+	int n_local, tile, ntiles, NWSG, KW, total_warps, dynamic;
+	int p, T, B, nCS, RP;
+	int S, NT;                // stride of the block decomposition, column tiles (8 NT >= S + 2)
+	double invL;
+	float inv_rVal;
+	int varbox;
+};
+struct MmaChoice {
+	int on;                   // 1: use the mma path for the real slots (the classic kernel then serves only rho)
+	int S, NT, SPW, UNR, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // SPW = origin slots per warp, UNR = slot loop unrolled
+	size_t smem;
+};
+int sqt_pick_mma(int nCS, int B, int n_local, int n_sm, MmaChoice *mc);
+int sqt_launch_mma(const MmaChoice &mc, const MmaArgs &a, cudaStream_t st);
+struct MmaReduceArgs {
+	const double *partial;
+	int KW, NWSG, S, NT, SPW;
+	int p, T, B, nCS;
+	int *tile_ctr;
+	int *hist_cur, *bufHist;
+	double *bufFs, *bufMSD, *bufMQD, *invL0;
+	double invL;
+};
+int sqt_launch_mma_reduce(const MmaReduceArgs &a, cudaStream_t st);
+
 // ---- kernels.cu ---------------------------------------------------------------------------
 // Picks (C, G, grid) for a deck; returns 0 or a cudaError_t.
 int sqt_pick_kernel(int nCS, int B, int n_local, int n_sm, KernelChoice *kc);

@@ -229,3 +229,57 @@ def test_deterministic_mode_is_bit_reproducible(monkeypatch):
     a, b = a.to_dict(), b.to_dict()
     for k in ("avF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "rrMSDAv", "rrMQDAv"):
         assert np.array_equal(a[k], b[k]), k
+
+
+# ---- FP64 tensor-core self path (sqt_mma.cu): nCSpatial >= 64 by default, SQT_MMA=1/0 forces it on/off ----------
+
+@pytest.mark.parametrize("S,spw", [(9, 4), (64, 4), (86, 2), (128, 8), (171, 4), (171, 2), (171, 8), (230, 4), (239, 4)])
+def test_tensor_core_self_path_matches_oracle(monkeypatch, S, spw):
+    """Blocked-Chebyshev self terms on DMMA: every column-tile count (S 9 -> 1 tile ... S 239 -> 4 tiles), every
+    slots-per-warp variant, ragged particle count (the last 32-particle tile is partial)."""
+    monkeypatch.setenv("SQT_MMA", "1")
+    monkeypatch.setenv("SQT_MMA_SPW", str(spw))
+    traj = synth.make_trajectory(n_cells=3, n_atoms=77, n_frames=30, seed=15)
+    got, raw, eng, _ = _run_both([traj], S, 9, 5)
+    assert "mma" in eng.kernel_config, eng.kernel_config
+    check_raw_sums(got, raw, traj.n_atoms, label="mma S%d spw%d " % (S, spw))
+    fd_identity(got)
+
+
+def test_tensor_core_path_fluctuating_box_two_files(monkeypatch):
+    monkeypatch.setenv("SQT_MMA", "1")
+    t1 = synth.make_trajectory(n_cells=3, n_atoms=50, n_frames=37, seed=3, box_jitter=0.01)
+    t2 = synth.make_trajectory(n_cells=3, n_atoms=50, n_frames=29, seed=4, box_jitter=0.01)
+    got, raw, eng, log = _run_both([t1, t2], 70, 8, 8, skip=1)
+    assert "mma" in eng.kernel_config
+    check_raw_sums(got, raw, 50, label="mma two files ")
+
+
+def test_tensor_core_path_agrees_with_classic_kernel(monkeypatch):
+    """Same frames through both self-term kernels: integer outputs identical, floating sums within round-off."""
+    traj = synth.make_trajectory(n_cells=4, n_frames=24, seed=8)
+    deck = Deck(limitCorrAv=BIG, nCBuffer=6, nCSpatial=100, nCTime=6)
+    monkeypatch.setenv("SQT_MMA", "0")
+    a, ea = run_trajectories([traj], deck)
+    assert "mma" not in ea.kernel_config
+    monkeypatch.setenv("SQT_MMA", "1")
+    b, eb = run_trajectories([traj], deck)
+    assert "mma" in eb.kernel_config
+    a, b = a.to_dict(), b.to_dict()
+    assert np.array_equal(a["avDrTable"], b["avDrTable"])
+    assert a["countCorrAv"] == b["countCorrAv"]
+    for k in ("avF_qq2", "avF_s_qq2", "rrMSDAv", "rrMQDAv"):
+        scale = np.abs(a[k]).max()
+        assert np.abs(a[k] - b[k]).max() <= 1e-11 * scale, k
+
+
+def test_tensor_core_path_deterministic_mode(monkeypatch):
+    monkeypatch.setenv("SQT_DETERMINISTIC", "1")
+    monkeypatch.setenv("SQT_MMA", "1")
+    traj = synth.make_trajectory(n_cells=4, n_frames=20, seed=33)
+    deck = Deck(limitCorrAv=BIG, nCBuffer=3, nCSpatial=70, nCTime=6)
+    a, _ = run_trajectories([traj], deck)
+    b, _ = run_trajectories([traj], deck)
+    a, b = a.to_dict(), b.to_dict()
+    for k in ("avF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "rrMSDAv", "rrMQDAv"):
+        assert np.array_equal(a[k], b[k]), k
