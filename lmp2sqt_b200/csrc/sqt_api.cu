@@ -45,6 +45,7 @@ struct sqt_handle {
 	bool copy_pending[2];
 	int stage_next;
 	double *d_ring;
+	long long ring_np;        // particle pitch of the [slot][axis][particle] ring (tensor-core path)
 	int RP;
 	double *d_partial;
 	int *d_tile_ctr;
@@ -59,6 +60,8 @@ struct sqt_handle {
 	KernelChoice kc;
 	MmaChoice mc;             // blocked-Chebyshev / DMMA path for the real slots (large nCSpatial)
 	double *d_mma_partial;
+	RhoMmaChoice rmc;
+	double *d_rho_partial;
 	int *d_mma_ctr;
 	cudaStream_t s_main, s_copy, s_coll;
 	cudaEvent_t ev_red, ev_coll, ev_t0, ev_t1;
@@ -154,7 +157,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->L = h->vol = h->first_vol = 0; h->kVal = p->kVal; h->first_limit = 0;
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
-	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->d_hist_cur = h->d_bufHist = nullptr;
+	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->rmc.on = 0; h->d_rho_partial = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
 	h->d_avblk = h->d_latblk = nullptr;
@@ -233,7 +236,7 @@ extern "C" void sqt_destroy(sqt_handle *h)
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_ring[i]) cudaEventDestroy(h->ev_ring[i]);
 	}
-	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
+	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr); cudaFree(h->d_rho_partial); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
 	cudaFree(h->d_bufFs); cudaFree(h->d_bufF); cudaFree(h->d_bufMSD); cudaFree(h->d_bufMQD); cudaFree(h->d_bufMSDCM);
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
@@ -306,7 +309,10 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 	rc = sqt_pick_kernel(h->S, h->mc.on ? 0 : h->B, n_local, h->n_sm, &h->kc);
 	if (rc != 0) return fail(h, SQT_ERR_CUDA, "no ring-kernel variant for nCSpatial=%d (rc=%d)", h->S, rc);
 	h->RP = (h->B + 15) & ~15; // 128-byte rows: a warp's 32 origins of one particle/axis are contiguous
-	const size_t ring_bytes = sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
+	// the tensor-core kernel walks particles along the warp, so its ring is [slot][axis][particle] (pitch: a multiple of 32
+	// particles); the classic kernel walks slots along the warp: [particle][axis][slot]
+	h->ring_np = ((long long)n_local + 31) & ~31LL;
+	const size_t ring_bytes = h->mc.on ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
 	cudaError_t e = cudaMalloc(&h->d_ring, ring_bytes);
 	if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin ring of %.2f GB does not fit on the device: %s", ring_bytes / 1e9, cudaGetErrorString(e));
 	CU(cudaMemsetAsync(h->d_ring, 0, ring_bytes, h->s_main));
@@ -322,6 +328,16 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 		CU(cudaMemsetAsync(h->d_mma_partial, 0, mma_bytes, h->s_main));
 		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * h->mc.NWSG));
 		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * h->mc.NWSG, h->s_main));
+		const char *rm = getenv("SQT_RHO_MMA");
+		if (!(rm && *rm == '0')) {
+			rc = sqt_pick_rho_mma(h->mc, n_local, h->n_sm, &h->rmc);
+			if (rc != 0) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel: %s", cudaGetErrorString((cudaError_t)rc));
+		}
+		if (h->rmc.on) {
+			const size_t rb = sizeof(double) * (size_t)h->rmc.total_warps * 6 * h->mc.NT * 64;
+			CU(cudaMalloc(&h->d_rho_partial, rb));
+			mma_bytes += rb;
+		}
 	}
 	int off = 0;
 	if (h->mc.on)
@@ -330,6 +346,9 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
 		               h->mc.NT, h->mc.SPW, h->mc.S, h->mc.blocks, h->mc.WPB * 32, h->mc.regs, h->mc.smem, h->mc.occ, h->mc.NWSG, h->mc.KW,
 		               h->mc.dynamic ? "dynamic" : "static", h->mc.tile);
+	if (h->rmc.on)
+		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles; unused: ",
+		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ);
 	snprintf(h->cfg + off, sizeof(h->cfg) - off,
 	         "self_ring_kernel<C=%d,G=%d> persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; %d slot groups x %d warps, "
 	         "%s tiles of %d particles (%d tiles); slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB",
@@ -373,14 +392,23 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
 		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local; ma.tile = h->mc.tile;
 		ma.ntiles = h->mc.ntiles; ma.NWSG = h->mc.NWSG; ma.KW = h->mc.KW; ma.total_warps = h->mc.total_warps; ma.dynamic = h->mc.dynamic;
-		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->RP; ma.S = h->mc.S; ma.NT = h->mc.NT; ma.invL = invL;
+		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = h->mc.S; ma.NT = h->mc.NT; ma.invL = invL;
 		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
 		rc = sqt_launch_mma(h->mc, ma, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
 	}
-	rc = sqt_launch_ring(h->kc, ra, h->s_main);
-	if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+	if (h->rmc.on) { // rho(k) and sum_n r on the tensor-core path too: the classic kernel is not launched at all
+		RhoMmaArgs qa;
+		qa.cur = h->d_cur[slot]; qa.partial = h->d_rho_partial; qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
+		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
+		rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+	} else {
+		rc = sqt_launch_ring(h->kc, ra, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+	}
 	if (h->prof) { CU(cudaEventRecord(pe1, h->s_main)); h->prof_ev.push_back(pe0); h->prof_ev.push_back(pe1); }
 	CU(cudaEventRecord(h->ev_ring[slot], h->s_main));
 	h->launches++;
@@ -400,9 +428,11 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		if (rc) return fail(h, SQT_ERR_CUDA, "mma_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
 	}
-	rc = sqt_launch_reduce(rr, h->s_main);
-	if (rc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-	h->launches++;
+	if (!h->rmc.on) {
+		rc = sqt_launch_reduce(rr, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+	}
 	if (split) {
 		CU(cudaEventRecord(h->ev_red, h->s_main));
 		CU(cudaStreamWaitEvent(h->s_coll, h->ev_red, 0));

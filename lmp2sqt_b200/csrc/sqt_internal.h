@@ -47,7 +47,7 @@ struct KernelChoice {
 // G is an (8 x 3N)(3N x 8 NT) product per origin slot, accumulated by mma.sync m8n8k4 f64.
 struct MmaArgs {
 	const double *cur;        // current frame, SoA [3][cur_pitch]
-	double *ring;             // origin positions [n][3][RP]
+	double *ring;             // origin positions [slot][3][RP], RP = particle pitch
 	double *partial;          // per-warp G fragments [slot group][k-th warp][SPW][NT][32 lanes][2]
 	int *tile_ctr;            // [NWSG]
 	int *hist_cur;            // [B][nCS]
@@ -55,7 +55,8 @@ struct MmaArgs {
 	const long long *thr;     // [nCS+2]
 	long long cur_pitch;
 	int n_local, tile, ntiles, NWSG, KW, total_warps, dynamic;
-	int p, T, B, nCS, RP;
+	int p, T, B, nCS;
+	long long RP;
 	int S, NT;                // stride of the block decomposition, column tiles (8 NT >= S + 2)
 	double invL;
 	float inv_rVal;
@@ -78,6 +79,17 @@ struct MmaReduceArgs {
 	double invL;
 };
 int sqt_launch_mma_reduce(const MmaReduceArgs &a, cudaStream_t st);
+struct RhoMmaArgs {
+	const double *cur;        // current frame, SoA [3][cur_pitch]
+	double *partial;          // per-warp fragments [warp][axis][cos|sin][NT][32 lanes][2]
+	double *rho_cur;          // [3][nCS][Re,Im] then sum_n r_a [3]
+	long long cur_pitch;
+	int n_local, total_warps, nCS, S, NT;
+	double invL;
+};
+struct RhoMmaChoice { int on, blocks, WPB, total_warps, occ; size_t smem; };
+int sqt_pick_rho_mma(const MmaChoice &mc, int n_local, int n_sm, RhoMmaChoice *rc);
+int sqt_launch_rho_mma(const MmaChoice &mc, const RhoMmaChoice &rc, const RhoMmaArgs &a, cudaStream_t st);
 
 // ---- kernels.cu ---------------------------------------------------------------------------
 // Picks (C, G, grid) for a deck; returns 0 or a cudaError_t.

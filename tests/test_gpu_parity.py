@@ -68,10 +68,12 @@ def test_bookkeeping_is_exact():
     eng.close()
 
 
-def test_rho_matches_oracle_each_frame():
+@pytest.mark.parametrize("S,mma", [(12, "0"), (12, "1"), (9, "1"), (64, "1"), (171, "1"), (171, "0"), (239, "1")])
+def test_rho_matches_oracle_each_frame(monkeypatch, S, mma):
+    """rho(k) after every frame, through the classic kernel's virtual slots and through the tensor-core rho kernel."""
     from lmp2sqt_b200 import SpacetimeCorr
-    traj = synth.make_trajectory(n_cells=3, n_frames=6, seed=9)
-    S = 12
+    monkeypatch.setenv("SQT_MMA", mma)
+    traj = synth.make_trajectory(n_cells=3, n_atoms=101, n_frames=6, seed=9, drift=(0.3, -0.2, 0.1))
     eng = SpacetimeCorr(Deck(limitCorrAv=BIG, nCBuffer=2, nCSpatial=S, nCTime=4))
     ora = pyoracle.OraclePort(S, 4, 2, limitCorrAv=BIG)
     eng.InitSpacetimeCorr(); ora.begin_file()
@@ -79,6 +81,7 @@ def test_rho_matches_oracle_each_frame():
         eng.EvalSpacetimeCorr(traj.positions[f], 0.0, traj.box[f, 0, 1])
         ora.push_frame(traj.positions[f], 0.0, traj.box[f, 0, 1])
         np.testing.assert_allclose(eng.rho(), ora.rho(), rtol=0, atol=1e-10 * traj.n_atoms)
+    assert ("rho_mma_kernel" in eng.kernel_config) == (mma == "1")
     eng.close()
 
 
