@@ -316,11 +316,24 @@ def main():
     units_per_launch = n_local * Kvec
     ach_tf = units_per_launch * flops_per_unit / (ring_ms_avg * 1e-3) / 1e12
     alg_bytes = n_local * 24.0 * (1 + B)             # current positions + B origin positions per particle
-    roofline = {"bound": "fp64_fma", "kernel": "self_ring_kernel", "achieved": ach_tf, "peak": dfma_tf, "unit": "TFLOP/s",
+    cfg_now = eng.kernel_config
+    on_mma = cfg_now.startswith("self_ring_mma_kernel")
+    family = "self_ring_mma_kernel" if on_mma else "self_ring_kernel"
+    if on_mma:
+        # what the tensor-core path executes instead of the recurrence: per (particle, origin, axis) an 8 x 8NT x 1 slice of
+        # the blocked-Chebyshev product on DMMA (the share of the FP64 pipe those DMMAs occupy is dmma_pipe_frac)
+        NT = int(cfg_now.split("NT=")[1].split(",")[0])
+        dmma_flops = n_local * 3.0 * (B * 2 * 8 * 8 * NT + 2 * 2 * 8 * 8 * NT)
+        pipe_note = {"dmma_flops_per_launch": dmma_flops, "dmma_pipe_frac": dmma_flops / (ring_ms_avg * 1e-3) / (dfma_tf * 1e12),
+                     "fp64_pipe_frac": None}
+    else:
+        pipe_note = {"fp64_pipe_frac": units_per_launch * (4 + 2 * B) / (ring_ms_avg * 1e-3) / (dfma_tf * 1e12 / 2.0)}
+    roofline = {"bound": "fp64_fma", "kernel": family + (" + rho_mma_kernel" if "rho_mma_kernel" in cfg_now else ""),
+                "achieved": ach_tf, "peak": dfma_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / dfma_tf, "traffic": None,
                 "peak_source": "measured live: register-resident DFMA microbenchmark (sqt_measure_dfma_peak), %.0f MHz implied" % dfma_mhz,
                 "flops_per_unit": flops_per_unit, "units_per_launch": units_per_launch, "avg_launch_ms": ring_ms_avg,
-                "fp64_pipe_frac": units_per_launch * (4 + 2 * B) / (ring_ms_avg * 1e-3) / (dfma_tf * 1e12 / 2.0),
+                **pipe_note,
                 "hbm": {"achieved": alg_bytes / (ring_ms_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (ring_ms_avg * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                         "algorithmic_bytes_per_launch": alg_bytes}}
@@ -329,7 +342,7 @@ def main():
         try:
             with open(prof_json) as f:
                 tr = json.load(f)
-            if tr.get("workload") == args.workload and tr.get("n_gpus") == world:
+            if tr.get("workload") == args.workload and tr.get("n_gpus") == world and tr.get("kernel", "").startswith(family + "<"):
                 roofline["traffic"] = tr.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -356,7 +369,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "atoms_total": n_total, "atoms_per_gpu": n_local, "K": Kvec,
                        "B_live": B, "parallelism": "particle-sharded x%d, per-frame NCCL allreduce of rho(k)" % world,
-                       "l2": "inputs larger than L2: the origin ring (%.1f GB per GPU) is streamed once per frame" % (3 * 160 * n_local * 8 / 1e9),
+                       "l2": "inputs larger than L2: the origin ring (%s per GPU) is streamed once per frame" % (cfg.split("ring=")[1].split(" ")[0] if "ring=" in cfg else "?"),
                        "kernel": cfg, "ring_fill_s": t_fill,
                        "pair_evals_per_sec": value * B},
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
