@@ -40,7 +40,7 @@ def _worker(rank, world, port, out_path, S, T, B, ncell, frames, flush_limit):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("S,T,B", [(6, 8, 4), (43, 6, 6)])
+@pytest.mark.parametrize("S,T,B", [(6, 8, 4), (43, 6, 6), (100, 6, 6)])  # the last one runs the tensor-core kernels
 def test_two_gpu_shards_match_single_gpu_and_oracle(tmp_path, S, T, B):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
