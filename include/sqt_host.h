@@ -65,7 +65,7 @@ int sqt_dump_skip_atoms(FILE *fp, const sqt_frame_header *hd);
  * (little endian, atoms in dump order).  It is recognised by its magic; sqt_raw_append_frame writes one frame. */
 typedef struct sqt_reader sqt_reader;
 sqt_reader *sqt_reader_open(const char *path, int n_threads);
-int sqt_reader_is_raw(const sqt_reader *r);
+int sqt_reader_is_raw(const sqt_reader *r); /* 0 LAMMPS text, 1 SQTRAW01 frame file, 2 LAMMPS native binary (`dump custom`, orthogonal box, id type xu yu zu ...) */
 int sqt_raw_append_frame(const char *path, int create, long long timestep, long long n_atoms, const double box[6],
                          const double *x, const double *y, const double *z);
 void sqt_reader_close(sqt_reader *r);

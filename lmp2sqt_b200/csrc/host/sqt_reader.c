@@ -27,7 +27,10 @@ struct sqt_reader {
 	const char *base;
 	size_t size, pos;
 	int fd, n_threads;
-	int raw;          /* 1: SQTRAW01 binary frame file (see sqt_host.h), 0: LAMMPS text dump */
+	int raw;          /* 0: LAMMPS text dump, 1: SQTRAW01 binary frame file (see sqt_host.h), 2: LAMMPS native binary dump */
+	/* LAMMPS binary: where the current frame's chunks start and how its rows are laid out */
+	size_t lb_chunks;
+	int lb_size_one, lb_nchunk, lb_col[3];
 };
 
 /* Raw binary frame file (extension, SURVEY.md section 8f.1 "raw f64[3][N] frame file"):
@@ -36,6 +39,116 @@ struct sqt_reader {
  * little endian, no padding.  Atom order is the dump order, exactly what the text path would deliver. */
 #define RAW_MAGIC "SQTRAW01"
 #define RAW_HDR (8 + 8 + 6 * 8)
+
+/* LAMMPS native binary dump (`dump custom ... file.bin`, what LAMMPS' own tools/binary2txt.cpp reads), little endian:
+ *   frame := [ int64 -len, char magic[len] ("DUMPCUSTOM"), int32 endian (1), int32 revision ]      (format since 2020; absent in older files)
+ *            int64 ntimestep, int64 natoms, int32 triclinic, int32 boundary[3][2], f64 xlo xhi ylo yhi zlo zhi, [f64 xy xz yz]
+ *            int32 size_one,
+ *            [ int32 len, char units[len], char time_flag, [f64 time], int32 len, char columns[len] ]   (revision > 1)
+ *            int32 nchunk, { int32 n, f64 buf[n] } * nchunk               (n / size_one atom rows per chunk, every field a double)
+ * Only what the text path accepts is accepted here: orthogonal box, columns `id type xu yu zu ...` (by name when the file
+ * carries names, by position otherwise), atoms in stored order (write the dump with `dump_modify sort id`, as the text
+ * path needs too: the reference identifies atoms by line order, snapshot.c:357-368). */
+typedef struct { const char *p, *e; int ok; } lb_cur;
+static void lb_get(lb_cur *c, void *dst, size_t n)
+{
+	if (!c->ok || (size_t)(c->e - c->p) < n) { c->ok = 0; memset(dst, 0, n); return; }
+	memcpy(dst, c->p, n);
+	c->p += n;
+}
+static void lb_skip(lb_cur *c, size_t n)
+{
+	if (!c->ok || (size_t)(c->e - c->p) < n) { c->ok = 0; return; }
+	c->p += n;
+}
+
+static int lb_next_header(sqt_reader *r, sqt_frame_header *hd)
+{
+	lb_cur c = { r->base + r->pos, r->base + r->size, 1 };
+	long long ntimestep = 0, natoms = 0;
+	int revision = 0, has_magic = 0;
+	lb_get(&c, &ntimestep, 8);
+	if (!c.ok) return 0;
+	if (ntimestep < 0) {
+		const long long mlen = -ntimestep;
+		if (mlen > 64) return 0;
+		char magic[65] = { 0 };
+		int endian = 0;
+		lb_get(&c, magic, (size_t)mlen);
+		lb_get(&c, &endian, 4);
+		lb_get(&c, &revision, 4);
+		lb_get(&c, &ntimestep, 8);
+		if (!c.ok || endian != 1 || strcmp(magic, "DUMPCUSTOM") != 0) return 0; /* `dump atom` files carry scaled coordinates */
+		has_magic = 1;
+	}
+	int triclinic = 0, boundary[6], size_one = 0, nchunk = 0;
+	double box[6];
+	lb_get(&c, &natoms, 8);
+	lb_get(&c, &triclinic, 4);
+	lb_get(&c, boundary, 24);
+	lb_get(&c, box, 48);
+	if (!c.ok || triclinic || natoms <= 0 || natoms > 2147483647LL) return 0;
+	lb_get(&c, &size_one, 4);
+	int col[3] = { 2, 3, 4 };
+	if (has_magic && revision > 1) {
+		int len = 0;
+		char flag = 0;
+		lb_get(&c, &len, 4);
+		if (len < 0) return 0;
+		lb_skip(&c, (size_t)len);                 /* unit style */
+		lb_get(&c, &flag, 1);
+		if (flag) lb_skip(&c, 8);                 /* simulation time */
+		lb_get(&c, &len, 4);
+		if (!c.ok || len < 0 || (size_t)(c.e - c.p) < (size_t)len) return 0;
+		/* column names: the reference's header test is the prefix "id type xu yu zu" (snapshot.c:296-331) */
+		static const char want[] = "id type xu yu zu";
+		if ((size_t)len < sizeof(want) - 1 || memcmp(c.p, want, sizeof(want) - 1) != 0) return 0;
+		lb_skip(&c, (size_t)len);
+	}
+	lb_get(&c, &nchunk, 4);
+	if (!c.ok || size_one < 5 || nchunk < 0) return 0;
+	memset(hd, 0, sizeof(*hd));
+	hd->timestep = (long)ntimestep; hd->n_atoms = (int)natoms;
+	hd->xlo = box[0]; hd->xhi = box[1]; hd->ylo = box[2]; hd->yhi = box[3]; hd->zlo = box[4]; hd->zhi = box[5];
+	hd->pbcType = (boundary[0] == 0 && boundary[1] == 0 ? 1 : 0) | (boundary[2] == 0 && boundary[3] == 0 ? 2 : 0) | (boundary[4] == 0 && boundary[5] == 0 ? 4 : 0);
+	hd->style = size_one >= 11 ? 3 : (size_one >= 8 ? 1 : 0);
+	r->lb_chunks = (size_t)(c.p - r->base);
+	r->lb_size_one = size_one; r->lb_nchunk = nchunk;
+	r->lb_col[0] = col[0]; r->lb_col[1] = col[1]; r->lb_col[2] = col[2];
+	r->pos = r->lb_chunks;
+	return 1;
+}
+
+/* walks the frame's chunks; with x != NULL scatters the coordinate columns into SoA.  1 ok / 0 short or inconsistent file */
+static int lb_walk_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z)
+{
+	lb_cur c = { r->base + r->lb_chunks, r->base + r->size, 1 };
+	const int so = r->lb_size_one, cx = r->lb_col[0], cy = r->lb_col[1], cz = r->lb_col[2];
+	long long row0 = 0;
+	for (int k = 0; k < r->lb_nchunk; k++) {
+		int n = 0;
+		lb_get(&c, &n, 4);
+		if (!c.ok || n < 0 || n % so != 0 || (size_t)(c.e - c.p) / 8 < (size_t)n) { r->pos = r->size; return 0; }
+		const long long rows = n / so;
+		if (row0 + rows > hd->n_atoms) { r->pos = r->size; return 0; }
+		if (x) {
+			const char *src = c.p;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(r->n_threads) schedule(static) if (rows > 65536)
+#endif
+			for (long long i = 0; i < rows; i++) {
+				const char *row = src + (size_t)i * so * 8;
+				memcpy(&x[row0 + i], row + 8 * cx, 8);
+				memcpy(&y[row0 + i], row + 8 * cy, 8);
+				memcpy(&z[row0 + i], row + 8 * cz, 8);
+			}
+		}
+		lb_skip(&c, (size_t)n * 8);
+		row0 += rows;
+	}
+	r->pos = (size_t)(c.p - r->base);
+	return row0 == hd->n_atoms;
+}
 
 static int starts_with(const char *p, const char *end, const char *prefix)
 {
@@ -144,6 +257,7 @@ sqt_reader *sqt_reader_open(const char *path, int n_threads)
 #endif
 	r->n_threads = n_threads < 1 ? 1 : n_threads;
 	if (r->size >= 8 && memcmp(r->base, RAW_MAGIC, 8) == 0) { r->raw = 1; r->pos = 8; }
+	else if (r->size >= 8 && memcmp(r->base, "ITEM:", 5) != 0) r->raw = 2; /* neither text nor SQTRAW01: LAMMPS native binary */
 	return r;
 }
 
@@ -155,7 +269,7 @@ void sqt_reader_close(sqt_reader *r)
 	free(r);
 }
 
-void sqt_reader_rewind(sqt_reader *r) { if (r) r->pos = r->raw ? 8 : 0; }
+void sqt_reader_rewind(sqt_reader *r) { if (r) r->pos = r->raw == 1 ? 8 : 0; }
 int sqt_reader_is_raw(const sqt_reader *r) { return r ? r->raw : 0; }
 
 int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd)
@@ -163,6 +277,7 @@ int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd)
 	const char *p, *e;
 	size_t pos = r->pos;
 	memset(hd, 0, sizeof(*hd));
+	if (r->raw == 2) return lb_next_header(r, hd);
 	if (r->raw) {
 		if (r->size - pos < RAW_HDR) return 0;
 		long long ts, n;
@@ -224,6 +339,7 @@ int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd)
 {
 	size_t endp, dummy;
 	if (hd->n_atoms <= 0) return 1;
+	if (r->raw == 2) return lb_walk_atoms(r, hd, NULL, NULL, NULL);
 	if (r->raw) { r->pos += (size_t)hd->n_atoms * 24; return 1; }
 	if (!index_lines(r, hd->n_atoms, hd->n_atoms, &dummy, 1, &endp)) { r->pos = r->size; return 0; }
 	r->pos = endp;
@@ -234,6 +350,7 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 {
 	const int n = hd->n_atoms;
 	if (n <= 0) return 1;
+	if (r->raw == 2) return lb_walk_atoms(r, hd, x, y, z);
 	if (r->raw) { /* already SoA: three straight copies into the staging buffer */
 		const char *src = r->base + r->pos;
 		memcpy(x, src, (size_t)n * 8); memcpy(y, src + (size_t)n * 8, (size_t)n * 8); memcpy(z, src + (size_t)n * 16, (size_t)n * 8);

@@ -196,3 +196,41 @@ def write_raw_dump(traj: Trajectory, path: str, frames: slice | None = None) -> 
         if rc:
             raise OSError("sqt_raw_append_frame failed for %s" % path)
         first = False
+
+
+def write_lammps_binary(traj: Trajectory, path: str, revision: int = 2, chunks: int = 2, frames: slice | None = None,
+                        columns: str = "id type xu yu zu", extra_cols: int = 0, triclinic: bool = False) -> None:
+    """Write ``traj`` in LAMMPS' native binary dump layout (what ``dump custom file.bin id type xu yu zu`` produces and
+    LAMMPS' tools/binary2txt.cpp reads; layout restated in csrc/host/sqt_reader.c).  ``revision`` 0 writes the pre-2020
+    layout without magic string and column names; ``chunks`` splits the atoms as a multi-rank run would."""
+    import struct
+    rng = range(traj.n_frames)[frames] if frames is not None else range(traj.n_frames)
+    n = traj.n_atoms
+    size_one = 5 + extra_cols
+    with open(path, "wb") as f:
+        for fi in rng:
+            if revision > 0:
+                magic = b"DUMPCUSTOM"
+                f.write(struct.pack("<q", -len(magic)) + magic + struct.pack("<ii", 1, revision))
+            f.write(struct.pack("<qq", int(traj.timesteps[fi]), n))
+            f.write(struct.pack("<i6i", int(triclinic), 0, 0, 0, 0, 0, 0))
+            b = traj.box[fi]
+            f.write(struct.pack("<6d", b[0, 0], b[0, 1], b[1, 0], b[1, 1], b[2, 0], b[2, 1]))
+            if triclinic:
+                f.write(struct.pack("<3d", 0.0, 0.0, 0.0))
+            f.write(struct.pack("<i", size_one))
+            if revision > 1:
+                units = b"lj"
+                cols = (columns + "".join(" c%d" % k for k in range(extra_cols))).encode()
+                f.write(struct.pack("<i", len(units)) + units + struct.pack("<b", 1) + struct.pack("<d", 0.005 * traj.timesteps[fi]))
+                f.write(struct.pack("<i", len(cols)) + cols)
+            rows = np.zeros((n, size_one))
+            rows[:, 0] = np.arange(1, n + 1)
+            rows[:, 1] = traj.types
+            rows[:, 2:5] = traj.positions[fi]
+            bounds = np.linspace(0, n, chunks + 1).astype(int)
+            f.write(struct.pack("<i", chunks))
+            for k in range(chunks):
+                blk = np.ascontiguousarray(rows[bounds[k]:bounds[k + 1]], dtype="<f8")
+                f.write(struct.pack("<i", blk.size))
+                f.write(blk.tobytes())

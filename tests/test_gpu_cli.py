@@ -106,15 +106,16 @@ def test_cli_raw_binary_dump_equals_text_dump(tmp_path):
     from lmp2sqt_b200 import synth
     t = synth.make_trajectory(n_cells=3, n_frames=45, seed=9)
     outs = {}
-    for kind in ("txt", "raw"):
+    for kind in ("txt", "raw", "lammpsbin"):
         d = tmp_path / kind
         d.mkdir()
         synth.write_deck(str(d / "in.lmp2sqt"), limitCorrAv=14825, nCBuffer=5, nCSpatial=7, nCTime=10)
-        dump = "dump.lammpstrj" if kind == "txt" else "dump.sqtraw"
-        (synth.write_text_dump if kind == "txt" else synth.write_raw_dump)(t, str(d / dump))
+        dump = {"txt": "dump.lammpstrj", "raw": "dump.sqtraw", "lammpsbin": "dump.bin"}[kind]
+        {"txt": synth.write_text_dump, "raw": synth.write_raw_dump, "lammpsbin": synth.write_lammps_binary}[kind](t, str(d / dump))
         r = subprocess.run([_lib.CLI_BIN, "-F", "-t", "-i", "in.lmp2sqt", dump], cwd=d, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-1000:]
         outs[kind] = pyoracle.parse_output_binary(str(d / "output.binary"), 7, 10)
-    for key in ("full-density", "self-density", "cross-density", "self-vanHove"):
-        np.testing.assert_allclose(outs["raw"][key], outs["txt"][key], rtol=1e-11, atol=1e-12)
-    assert (tmp_path / "raw" / "in.lmp2sqt").read_bytes() == (tmp_path / "txt" / "in.lmp2sqt").read_bytes()
+    for kind in ("raw", "lammpsbin"):
+        for key in ("full-density", "self-density", "cross-density", "self-vanHove"):
+            np.testing.assert_allclose(outs[kind][key], outs["txt"][key], rtol=1e-11, atol=1e-12)
+        assert (tmp_path / kind / "in.lmp2sqt").read_bytes() == (tmp_path / "txt" / "in.lmp2sqt").read_bytes()

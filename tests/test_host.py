@@ -268,3 +268,44 @@ def test_raw_binary_frame_file_equals_text_dump(tmp_path):
     data = (tmp_path / "d.sqtraw").read_bytes()
     (tmp_path / "cut.sqtraw").write_bytes(data[:-100])          # truncated last frame is not delivered
     assert len(_read_all_frames_mmap(str(tmp_path / "cut.sqtraw"), 1)) == 5
+
+
+@pytest.mark.parametrize("revision,chunks,extra", [(2, 3, 0), (2, 1, 3), (1, 2, 0), (0, 2, 0)])
+def test_lammps_native_binary_dump_equals_text_dump(tmp_path, revision, chunks, extra):
+    """SURVEY.md 8f.1, extension pinned by self-consistency: LAMMPS' native binary dump layout (current and pre-2020
+    headers, several per-rank chunks, extra per-atom columns) delivers exactly what the text dump delivers."""
+    t = synth.make_trajectory(n_cells=3, n_atoms=91, n_frames=6, seed=14, box_jitter=0.01)
+    synth.write_text_dump(t, str(tmp_path / "d.lammpstrj"))
+    synth.write_lammps_binary(t, str(tmp_path / "d.bin"), revision=revision, chunks=chunks, extra_cols=extra)
+    a = _read_all_frames_mmap(str(tmp_path / "d.lammpstrj"), 2)
+    b = _read_all_frames_mmap(str(tmp_path / "d.bin"), 2)
+    assert len(a) == len(b) == 6
+    for (ts1, n1, box1, x1), (ts2, n2, box2, x2) in zip(a, b):
+        assert (ts1, n1, box1) == (ts2, n2, box2) and np.array_equal(x1, x2)
+    h = _lib.host_lib()
+    r = h.sqt_reader_open(str(tmp_path / "d.bin").encode(), 1)
+    assert h.sqt_reader_is_raw(r) == 2
+    hd = SqtFrameHeader()
+    n = 0
+    while h.sqt_reader_next_header(r, C.byref(hd)) and h.sqt_reader_skip_atoms(r, C.byref(hd)):
+        n += 1
+    h.sqt_reader_rewind(r)
+    assert h.sqt_reader_next_header(r, C.byref(hd)) == 1 and hd.timestep == 0 and hd.n_atoms == 91 and hd.pbcType == 7
+    h.sqt_reader_close(r)
+    assert n == 6
+    data = (tmp_path / "d.bin").read_bytes()
+    (tmp_path / "cut.bin").write_bytes(data[:-100])                # truncated last frame is not delivered
+    assert len(_read_all_frames_mmap(str(tmp_path / "cut.bin"), 1)) == 5
+
+
+def test_lammps_native_binary_rejects_what_the_text_reader_rejects(tmp_path):
+    """Triclinic boxes, `dump atom` files and other column orders stop the file like an unknown text header does
+    (snapshot.c:296-331)."""
+    t = synth.make_trajectory(n_cells=2, n_frames=3, seed=1)
+    synth.write_lammps_binary(t, str(tmp_path / "tri.bin"), triclinic=True)
+    synth.write_lammps_binary(t, str(tmp_path / "cols.bin"), columns="id type x y z")
+    assert _read_all_frames_mmap(str(tmp_path / "tri.bin"), 1) == []
+    assert _read_all_frames_mmap(str(tmp_path / "cols.bin"), 1) == []
+    data = (tmp_path / "tri.bin").read_bytes()
+    (tmp_path / "atom.bin").write_bytes(data.replace(b"DUMPCUSTOM", b"DUMPATOMXX"))
+    assert _read_all_frames_mmap(str(tmp_path / "atom.bin"), 1) == []
