@@ -84,6 +84,31 @@ void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_
 int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t,
                            const char *date);
 
+/* ---- post-processing of the correlators (reference: analysis_binary.c) ---------------------
+ * Tables are [k][t] (k-major) like the reference's corrSum.  Sequence: load (or from_results) -> time | fourier -> print. */
+#define SQT_AN_TYPES 4 /* full-density, self-density, cross-density, self-vanHove */
+typedef struct {
+	int nCSpatial, nCTime, nData;      /* nData = sets of output.binary that were averaged */
+	double deck_deltaT;                /* deltaT of the deck: the time axis of the printed tables (deltaTCorr, analysis_binary.c:430) */
+	double deltaT, kVal, rVal;         /* from the block headers of output.binary (deltaT*(nCSkip+1), 2 pi/L, rVal) */
+	double *mean[SQT_AN_TYPES], *sd[SQT_AN_TYPES], *err[SQT_AN_TYPES]; /* corrSum / corrSumSq / corrSumErr */
+	double *F[SQT_AN_TYPES], *F1[SQT_AN_TYPES], *Gamma[SQT_AN_TYPES];  /* F(q,t), dF/dt, d ln F/dt */
+	double *D[SQT_AN_TYPES], *Dc[SQT_AN_TYPES], *H[SQT_AN_TYPES], *Hc[SQT_AN_TYPES]; /* -Gamma/q^2, -ln(F/F0)/(q^2 t), times F0 */
+	int fourier, omegaMax, nv;
+	double tMax;
+} sqt_analysis;
+/* import_settings + load_raw_data + scaling_data (analysis_binary.c:407-447, 643-771).  0 ok, <0 error. */
+int sqt_analysis_load(sqt_analysis *a, const char *deck_path, const char *binary_path, int nSetSkip);
+/* Same tables straight from results fetched from the engine and normalised by sqt_host_normalise (one set). */
+int sqt_analysis_from_results(sqt_analysis *a, const sqt_results *normalised, const sqt_deck *d, int flag_F);
+/* do_not_fourier (:793-897): derivative tables, "<block>00.out" summaries into outdir (NULL = cwd), scaling by F(q,0). */
+int sqt_analysis_time(sqt_analysis *a, int nValDiff, double under_limit, const char *outdir);
+/* do_fourier (:772-792): cosine transform of the first three blocks; 2 (nCTime - 1) must be a power of two. */
+int sqt_analysis_fourier(sqt_analysis *a, int window);
+/* print_output (:898-963): Fq?_scaled, Fq?, GammaQ?, Dq?_c, Dq?, D0Hq?_c, D0Hq?, Fq?1 `.<block>.info` files, %.13e. */
+int sqt_analysis_print(const sqt_analysis *a, const char *outdir);
+void sqt_analysis_free(sqt_analysis *a);
+
 #ifdef __cplusplus
 }
 #endif

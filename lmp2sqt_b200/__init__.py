@@ -7,6 +7,7 @@ bindings, a Python mirror of the reference's call seam, the synthetic-dump gener
 from .engine import (Deck, Results, SpacetimeCorr, SqtError, SynthSource, comm_unique_id,  # noqa: F401
                      measure_dfma_peak, run_trajectories, shard_bounds)
 from ._lib import SQT_FLUSH, SQT_OK  # noqa: F401
+from .analysis import Analysis  # noqa: F401
 
-__all__ = ["Deck", "Results", "SpacetimeCorr", "SqtError", "SynthSource", "comm_unique_id", "measure_dfma_peak",
+__all__ = ["Analysis", "Deck", "Results", "SpacetimeCorr", "SqtError", "SynthSource", "comm_unique_id", "measure_dfma_peak",
            "run_trajectories", "shard_bounds", "SQT_FLUSH", "SQT_OK"]

@@ -12,6 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ENGINE_SO = os.path.join(PKG_DIR, "libsqt_b200.so")
 HOST_SO = os.path.join(PKG_DIR, "libsqt_host.so")
 CLI_BIN = os.path.join(PKG_DIR, "bin", "lmp2sqt_b200.out")
+ANALYSIS_BIN = os.path.join(PKG_DIR, "bin", "analysis_binary_b200.out")
 
 SQT_OK, SQT_FLUSH = 0, 1
 SQT_COMM_ID_BYTES = 128
@@ -46,6 +47,15 @@ class SqtFrameHeader(C.Structure):
     _fields_ = [("timestep", C.c_long), ("n_atoms", C.c_int), ("xlo", C.c_double), ("xhi", C.c_double),
                 ("ylo", C.c_double), ("yhi", C.c_double), ("zlo", C.c_double), ("zhi", C.c_double),
                 ("pbcType", C.c_int), ("style", C.c_int)]
+
+
+class SqtAnalysis(C.Structure):
+    _fields_ = [("nCSpatial", C.c_int), ("nCTime", C.c_int), ("nData", C.c_int),
+                ("deck_deltaT", C.c_double), ("deltaT", C.c_double), ("kVal", C.c_double), ("rVal", C.c_double),
+                ("mean", _PD * 4), ("sd", _PD * 4), ("err", _PD * 4),
+                ("F", _PD * 4), ("F1", _PD * 4), ("Gamma", _PD * 4),
+                ("D", _PD * 4), ("Dc", _PD * 4), ("H", _PD * 4), ("Hc", _PD * 4),
+                ("fourier", C.c_int), ("omegaMax", C.c_int), ("nv", C.c_int), ("tMax", C.c_double)]
 
 
 # every symbol include/sqt.h declares: (name, restype, argtypes)
@@ -103,6 +113,12 @@ HOST_API = [
     ("sqt_host_factor_dr", None, [C.POINTER(SqtResults), C.c_double, C.c_void_p]),
     ("sqt_host_normalise", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int]),
     ("sqt_host_print_process", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    ("sqt_analysis_load", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p, C.c_char_p, C.c_int]),
+    ("sqt_analysis_from_results", C.c_int, [C.POINTER(SqtAnalysis), C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int]),
+    ("sqt_analysis_time", C.c_int, [C.POINTER(SqtAnalysis), C.c_int, C.c_double, C.c_char_p]),
+    ("sqt_analysis_fourier", C.c_int, [C.POINTER(SqtAnalysis), C.c_int]),
+    ("sqt_analysis_print", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p]),
+    ("sqt_analysis_free", None, [C.POINTER(SqtAnalysis)]),
 ]
 
 

@@ -119,3 +119,34 @@ def test_cli_raw_binary_dump_equals_text_dump(tmp_path):
         for key in ("full-density", "self-density", "cross-density", "self-vanHove"):
             np.testing.assert_allclose(outs[kind][key], outs["txt"][key], rtol=1e-11, atol=1e-12)
         assert (tmp_path / kind / "in.lmp2sqt").read_bytes() == (tmp_path / "txt" / "in.lmp2sqt").read_bytes()
+
+
+def test_analysis_on_device_results_equals_the_file_chain(tmp_path, monkeypatch):
+    """the post-processing pipeline applied directly to results fetched from the engine gives the same
+    files as CLI -> output.binary -> analysis CLI (and those equal the reference's, tests/test_analysis.py)."""
+    from lmp2sqt_b200 import Deck, run_trajectories, synth
+    from lmp2sqt_b200.analysis import Analysis
+    S, T, B = 70, 9, 9                                     # nCSpatial 70: the tensor-core kernels produce the correlators
+    monkeypatch.setenv("SQT_DETERMINISTIC", "1")           # both routes sum in the same order: the files must agree to the last digit
+    t = synth.make_trajectory(n_cells=3, n_frames=40, seed=23)
+    d = tmp_path / "chain"
+    d.mkdir()
+    synth.write_deck(str(d / "in.lmp2sqt"), limitCorrAv=14825, nCBuffer=B, nCSpatial=S, nCTime=T)
+    synth.write_text_dump(t, str(d / "dump.lammpstrj"))
+    r = subprocess.run([_lib.CLI_BIN, "-F", "-t", "-i", "in.lmp2sqt", "dump.lammpstrj"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    r = subprocess.run([_lib.ANALYSIS_BIN, "output.binary"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    deck = Deck(limitCorrAv=14825, nCBuffer=B, nCSpatial=S, nCTime=T)  # run_trajectories adds the computed part like the CLI does
+    res, eng = run_trajectories([t], deck, "Ft")
+    res.normalise(deck, "Ft")
+    o = tmp_path / "direct"
+    o.mkdir()
+    Analysis.from_results(res, deck, "Ft").time(outdir=str(o)).print(str(o))
+    names = sorted(f for f in os.listdir(o))
+    assert len(names) == 30
+    for f in names:
+        a, b = (o / f).read_text().split(), (d / f).read_text().split()
+        assert len(a) == len(b), f
+        for x, y in zip(a, b):
+            assert x == y or ("nan" in x and "nan" in y), (f, x, y)
