@@ -62,6 +62,7 @@ struct sqt_handle {
 	double *d_mma_partial;
 	RhoMmaChoice rmc;
 	double *d_rho_partial;
+	double *d_mma_extra, *d_rho_extra; // per-warp sums kept outside the DMMA product (MmaChoice.SPOUT)
 	int *d_mma_ctr;
 	cudaStream_t s_main, s_copy, s_coll;
 	cudaEvent_t ev_red, ev_coll, ev_t0, ev_t1;
@@ -157,7 +158,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->L = h->vol = h->first_vol = 0; h->kVal = p->kVal; h->first_limit = 0;
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
-	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->rmc.on = 0; h->d_rho_partial = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
+	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->rmc.on = 0; h->d_rho_partial = nullptr; h->d_mma_extra = h->d_rho_extra = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
 	h->d_avblk = h->d_latblk = nullptr;
@@ -236,7 +237,7 @@ extern "C" void sqt_destroy(sqt_handle *h)
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_ring[i]) cudaEventDestroy(h->ev_ring[i]);
 	}
-	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr); cudaFree(h->d_rho_partial); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
+	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr); cudaFree(h->d_rho_partial); cudaFree(h->d_mma_extra); cudaFree(h->d_rho_extra); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
 	cudaFree(h->d_bufFs); cudaFree(h->d_bufF); cudaFree(h->d_bufMSD); cudaFree(h->d_bufMQD); cudaFree(h->d_bufMSDCM);
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
@@ -328,6 +329,9 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 		CU(cudaMemsetAsync(h->d_mma_partial, 0, mma_bytes, h->s_main));
 		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * h->mc.NWSG));
 		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * h->mc.NWSG, h->s_main));
+		const size_t xb = sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * 2;
+		CU(cudaMalloc(&h->d_mma_extra, xb));
+		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
 		const char *rm = getenv("SQT_RHO_MMA");
 		if (!(rm && *rm == '0')) {
 			rc = sqt_pick_rho_mma(h->mc, n_local, h->n_sm, &h->rmc);
@@ -336,15 +340,16 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 		if (h->rmc.on) {
 			const size_t rb = sizeof(double) * (size_t)h->rmc.total_warps * 6 * h->mc.NT * 64;
 			CU(cudaMalloc(&h->d_rho_partial, rb));
+			CU(cudaMalloc(&h->d_rho_extra, sizeof(double) * (size_t)h->rmc.total_warps * 3));
 			mma_bytes += rb;
 		}
 	}
 	int off = 0;
 	if (h->mc.on)
 		off = snprintf(h->cfg, sizeof(h->cfg),
-		               "self_ring_mma_kernel<NT=%d,SPW=%d> (blocked Chebyshev S=%d on DMMA) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
+		               "self_ring_mma_kernel<NT=%d,SPW=%d> (blocked Chebyshev S=%d on DMMA%s) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
 		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
-		               h->mc.NT, h->mc.SPW, h->mc.S, h->mc.blocks, h->mc.WPB * 32, h->mc.regs, h->mc.smem, h->mc.occ, h->mc.NWSG, h->mc.KW,
+		               h->mc.NT, h->mc.SPW, h->mc.S, h->mc.SPOUT ? ", MSD/MQD outside" : "", h->mc.blocks, h->mc.WPB * 32, h->mc.regs, h->mc.smem, h->mc.occ, h->mc.NWSG, h->mc.KW,
 		               h->mc.dynamic ? "dynamic" : "static", h->mc.tile);
 	if (h->rmc.on)
 		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles; unused: ",
@@ -389,7 +394,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	int rc;
 	if (h->mc.on) {
 		MmaArgs ma;
-		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
 		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local; ma.tile = h->mc.tile;
 		ma.ntiles = h->mc.ntiles; ma.NWSG = h->mc.NWSG; ma.KW = h->mc.KW; ma.total_warps = h->mc.total_warps; ma.dynamic = h->mc.dynamic;
 		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = h->mc.S; ma.NT = h->mc.NT; ma.invL = invL;
@@ -400,7 +405,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	}
 	if (h->rmc.on) { // rho(k) and sum_n r on the tensor-core path too: the classic kernel is not launched at all
 		RhoMmaArgs qa;
-		qa.cur = h->d_cur[slot]; qa.partial = h->d_rho_partial; qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
+		qa.cur = h->d_cur[slot]; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT; qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
 		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
 		rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -421,7 +426,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.rho_cur = h->d_rho_cur; rr.invL0 = h->d_invL0; rr.invL = invL;
 	if (h->mc.on) {
 		MmaReduceArgs mr;
-		mr.partial = h->d_mma_partial; mr.KW = h->mc.KW; mr.NWSG = h->mc.NWSG; mr.S = h->mc.S; mr.NT = h->mc.NT; mr.SPW = h->mc.SPW;
+		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = h->mc.SPOUT; mr.n_local = h->n_local; mr.KW = h->mc.KW; mr.NWSG = h->mc.NWSG; mr.S = h->mc.S; mr.NT = h->mc.NT; mr.SPW = h->mc.SPW;
 		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
 		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
 		rc = sqt_launch_mma_reduce(mr, h->s_main);

@@ -49,6 +49,7 @@ struct MmaArgs {
 	const double *cur;        // current frame, SoA [3][cur_pitch]
 	double *ring;             // origin positions [slot][3][RP], RP = particle pitch
 	double *partial;          // per-warp G fragments [slot group][k-th warp][SPW][NT][32 lanes][2]
+	double *extra;            // SPOUT: per-warp (MSD, MQD) sums [slot group][k-th warp][SPW][2]
 	int *tile_ctr;            // [NWSG]
 	int *hist_cur;            // [B][nCS]
 	const double *invL0;      // [B]
@@ -64,14 +65,14 @@ struct MmaArgs {
 };
 struct MmaChoice {
 	int on;                   // 1: use the mma path for the real slots (the classic kernel then serves only rho)
-	int S, NT, SPW, UNR, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // SPW = origin slots per warp, UNR = slot loop unrolled
+	int S, NT, SPW, SPOUT, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // SPW = origin slots per warp, SPOUT = MSD/MQD summed outside the product
 	size_t smem;
 };
 int sqt_pick_mma(int nCS, int B, int n_local, int n_sm, MmaChoice *mc);
 int sqt_launch_mma(const MmaChoice &mc, const MmaArgs &a, cudaStream_t st);
 struct MmaReduceArgs {
-	const double *partial;
-	int KW, NWSG, S, NT, SPW;
+	const double *partial, *extra;
+	int KW, NWSG, S, NT, SPW, spout, n_local;
 	int p, T, B, nCS;
 	int *tile_ctr;
 	int *hist_cur, *bufHist;
@@ -84,7 +85,8 @@ struct RhoMmaArgs {
 	double *partial;          // per-warp fragments [warp][axis][cos|sin][NT][32 lanes][2]
 	double *rho_cur;          // [3][nCS][Re,Im] then sum_n r_a [3]
 	long long cur_pitch;
-	int n_local, total_warps, nCS, S, NT;
+	double *extra;            // SPOUT: per-warp sum_n r_a [warp][3]
+	int n_local, total_warps, nCS, S, NT, spout;
 	double invL;
 };
 struct RhoMmaChoice { int on, blocks, WPB, total_warps, occ; size_t smem; };

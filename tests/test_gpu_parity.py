@@ -68,7 +68,7 @@ def test_bookkeeping_is_exact():
     eng.close()
 
 
-@pytest.mark.parametrize("S,mma", [(12, "0"), (12, "1"), (9, "1"), (64, "1"), (171, "1"), (171, "0"), (239, "1")])
+@pytest.mark.parametrize("S,mma", [(12, "0"), (12, "1"), (9, "1"), (64, "1"), (128, "1"), (171, "1"), (171, "0"), (239, "1"), (256, "1")])
 def test_rho_matches_oracle_each_frame(monkeypatch, S, mma):
     """rho(k) after every frame, through the classic kernel's virtual slots and through the tensor-core rho kernel."""
     from lmp2sqt_b200 import SpacetimeCorr
@@ -236,7 +236,7 @@ def test_deterministic_mode_is_bit_reproducible(monkeypatch):
 
 # ---- FP64 tensor-core self path (sqt_mma.cu): nCSpatial >= 64 by default, SQT_MMA=1/0 forces it on/off ----------
 
-@pytest.mark.parametrize("S,spw", [(9, 4), (64, 4), (86, 2), (128, 8), (171, 4), (171, 2), (171, 8), (230, 4), (239, 4)])
+@pytest.mark.parametrize("S,spw", [(9, 4), (64, 4), (64, 2), (86, 2), (120, 2), (128, 2), (128, 4), (171, 4), (171, 2), (192, 2), (230, 4), (240, 4), (256, 2)])
 def test_tensor_core_self_path_matches_oracle(monkeypatch, S, spw):
     """Blocked-Chebyshev self terms on DMMA: every column-tile count (S 9 -> 1 tile ... S 239 -> 4 tiles), every
     slots-per-warp variant, ragged particle count (the last 32-particle tile is partial)."""
