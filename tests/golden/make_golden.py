@@ -44,6 +44,9 @@ CASES = {
     "g4_collective_only": dict(traj=[dict(n_cells=2, n_frames=33, seed=5)], S=5, T=6, B=3, skip=None, limit=14825, flags="ft"),
     # in.lmp2sqt.150.smallQ-like ring (T = B = 150 is too slow for a fixture; 30/30 keeps the shape)
     "g5_ring30": dict(traj=[dict(n_cells=3, n_frames=100, seed=6)], S=10, T=30, B=30, skip=None, limit=14825, flags="Ft"),
+    # nCSpatial in the range the tensor-core kernels serve (>= 64); 128 = the second column layout, config 4's nCSpatial
+    "g6_nCS70": dict(traj=[dict(n_cells=3, n_atoms=100, n_frames=36, seed=7, box_jitter=0.005)], S=70, T=8, B=8, skip=None, limit=14825, flags="Ft"),
+    "g7_nCS128": dict(traj=[dict(n_cells=3, n_frames=30, seed=8)], S=128, T=6, B=3, skip=None, limit=14825, flags="Ft"),
 }
 
 
@@ -51,7 +54,10 @@ def main():
     pyoracle.build()
     assert pyoracle.have_reference(), "needs /root/reference"
     here = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]                                   # optional: regenerate just the named cases
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         out = os.path.join(here, name)
         shutil.rmtree(out, ignore_errors=True)
         os.makedirs(out)
