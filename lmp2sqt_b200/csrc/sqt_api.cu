@@ -406,7 +406,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	if (h->rmc.on) { // rho(k) and sum_n r on the tensor-core path too: the classic kernel is not launched at all
 		RhoMmaArgs qa;
 		qa.cur = h->d_cur[slot]; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT; qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
-		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
+		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.n_sets = h->rmc.blocks; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
 		rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;

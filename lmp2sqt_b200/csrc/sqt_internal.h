@@ -82,11 +82,11 @@ struct MmaReduceArgs {
 int sqt_launch_mma_reduce(const MmaReduceArgs &a, cudaStream_t st);
 struct RhoMmaArgs {
 	const double *cur;        // current frame, SoA [3][cur_pitch]
-	double *partial;          // per-warp fragments [warp][axis][cos|sin][NT][32 lanes][2]
+	double *partial;          // per-block fragments [block][axis][cos|sin][NT][32 lanes][2]
 	double *rho_cur;          // [3][nCS][Re,Im] then sum_n r_a [3]
 	long long cur_pitch;
-	double *extra;            // SPOUT: per-warp sum_n r_a [warp][3]
-	int n_local, total_warps, nCS, S, NT, spout;
+	double *extra;            // SPOUT: per-block sum_n r_a [block][3]
+	int n_local, total_warps, n_sets, nCS, S, NT, spout; // n_sets = blocks = partial sets
 	double invL;
 };
 struct RhoMmaChoice { int on, blocks, WPB, total_warps, occ; size_t smem; };

@@ -9,7 +9,7 @@ _lib.ENGINE_SO = os.path.join(ROOT, "lmp2sqt_b200", "libsqt_b200_timing.so")
 from lmp2sqt_b200 import Deck, SpacetimeCorr, SynthSource
 lib = _lib.engine_lib()
 n_cells = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-S, T, B = 171, 150, 150
+S, T, B = (int(sys.argv[2]) if len(sys.argv) > 2 else 171), 150, 150
 n = 4 * n_cells ** 3
 eng = SpacetimeCorr(Deck(limitCorrAv=10**9, nCBuffer=B, nCSpatial=S, nCTime=T)); src = SynthSource(n_cells, 0, n)
 eng.InitSpacetimeCorr()
