@@ -61,6 +61,7 @@ struct sqt_handle {
 	MmaChoice mc;             // blocked-Chebyshev / DMMA path for the real slots (large nCSpatial)
 	double *d_mma_partial;
 	RhoMmaChoice rmc;
+	VecChoice vc;             // particle-per-lane vector kernel (nCSpatial <= 32)
 	double *d_rho_partial;
 	double *d_mma_extra, *d_rho_extra; // per-warp sums kept outside the DMMA product (MmaChoice.SPOUT)
 	int *d_mma_ctr;
@@ -158,7 +159,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->L = h->vol = h->first_vol = 0; h->kVal = p->kVal; h->first_limit = 0;
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
-	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->rmc.on = 0; h->d_rho_partial = nullptr; h->d_mma_extra = h->d_rho_extra = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
+	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->mc.geo = 0; h->vc.on = 0; h->rmc.on = 0; h->d_rho_partial = nullptr; h->d_mma_extra = h->d_rho_extra = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
 	h->d_avblk = h->d_latblk = nullptr;
@@ -306,14 +307,20 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 	for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_cur[i], sizeof(double) * 3 * h->cur_pitch));
 	int rc = sqt_pick_mma(h->S, h->B, n_local, h->n_sm, &h->mc);
 	if (rc != 0) return fail(h, SQT_ERR_CUDA, "mma kernel selection failed (rc=%d)", rc);
-	// with the mma path on, the classic kernel serves only the six virtual rho(k) slots (B = 0 for it)
-	rc = sqt_pick_kernel(h->S, h->mc.on ? 0 : h->B, n_local, h->n_sm, &h->kc);
+	if (!h->mc.on) {
+		rc = sqt_pick_vec(h->S, h->B, n_local, h->n_sm, &h->vc);
+		if (rc != 0) return fail(h, SQT_ERR_CUDA, "vector kernel selection failed (rc=%d)", rc);
+		if (h->vc.on && !h->mc.geo) h->vc.on = 0; // rho(k) comes from the tensor-core rho kernel on this path
+	}
+	const bool lane_family = h->mc.on || h->vc.on; // a particle per lane: particle-minor ring, rho(k) from rho_mma_kernel
+	// with a particle-per-lane self kernel on, the classic kernel serves at most the six virtual rho(k) slots (B = 0 for it)
+	rc = sqt_pick_kernel(h->S, lane_family ? 0 : h->B, n_local, h->n_sm, &h->kc);
 	if (rc != 0) return fail(h, SQT_ERR_CUDA, "no ring-kernel variant for nCSpatial=%d (rc=%d)", h->S, rc);
 	h->RP = (h->B + 15) & ~15; // 128-byte rows: a warp's 32 origins of one particle/axis are contiguous
 	// the tensor-core kernel walks particles along the warp, so its ring is [slot][axis][particle] (pitch: a multiple of 32
 	// particles); the classic kernel walks slots along the warp: [particle][axis][slot]
 	h->ring_np = ((long long)n_local + 31) & ~31LL;
-	const size_t ring_bytes = h->mc.on ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
+	const size_t ring_bytes = lane_family ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
 	cudaError_t e = cudaMalloc(&h->d_ring, ring_bytes);
 	if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin ring of %.2f GB does not fit on the device: %s", ring_bytes / 1e9, cudaGetErrorString(e));
 	CU(cudaMemsetAsync(h->d_ring, 0, ring_bytes, h->s_main));
@@ -323,13 +330,15 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 	CU(cudaMalloc(&h->d_tile_ctr, sizeof(int) * h->kc.NWSG));
 	CU(cudaMemsetAsync(h->d_tile_ctr, 0, sizeof(int) * h->kc.NWSG, h->s_main));
 	size_t mma_bytes = 0;
-	if (h->mc.on) {
-		mma_bytes = sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * h->mc.NT * 64;
+	if (lane_family) {
+		const int nwsg = h->mc.on ? h->mc.NWSG : h->vc.NWSG;
+		mma_bytes = h->mc.on ? sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * h->mc.NT * 64
+		                     : sizeof(double) * (size_t)h->vc.NWSG * h->vc.KW * h->vc.SPW * (h->vc.C + 2);
 		CU(cudaMalloc(&h->d_mma_partial, mma_bytes));
 		CU(cudaMemsetAsync(h->d_mma_partial, 0, mma_bytes, h->s_main));
-		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * h->mc.NWSG));
-		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * h->mc.NWSG, h->s_main));
-		const size_t xb = sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * 2;
+		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * nwsg));
+		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * nwsg, h->s_main));
+		const size_t xb = h->mc.on ? sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * 2 : 16;
 		CU(cudaMalloc(&h->d_mma_extra, xb));
 		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
 		const char *rm = getenv("SQT_RHO_MMA");
@@ -345,6 +354,12 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 		}
 	}
 	int off = 0;
+	if (h->vc.on)
+		off = snprintf(h->cfg, sizeof(h->cfg),
+		               "self_ring_vec_kernel<C=%d,SPW=%d> (a particle per lane, sums in registers) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
+		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
+		               h->vc.C, h->vc.SPW, h->vc.blocks, h->vc.WPB * 32, h->vc.regs, h->vc.smem, h->vc.occ, h->vc.NWSG, h->vc.KW,
+		               h->vc.dynamic ? "dynamic" : "static", h->vc.tile);
 	if (h->mc.on)
 		off = snprintf(h->cfg, sizeof(h->cfg),
 		               "self_ring_mma_kernel<NT=%d,SPW=%d> (blocked Chebyshev S=%d on DMMA%s) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
@@ -378,7 +393,7 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	for (int nb = 0; nb < B; ++nb)
 		if (h->count[nb] > 0 && h->h_invL0[nb] != invL) { varbox = 1; break; }
 
-	const int Bc = h->mc.on ? 0 : B; // slots the classic kernel treats as real
+	const int Bc = (h->mc.on || h->vc.on) ? 0 : B; // slots the classic kernel treats as real
 	RingArgs ra;
 	ra.cur = h->d_cur[slot]; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
 	ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = h->cur_pitch; ra.n_local = h->n_local;
@@ -392,6 +407,17 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		CU(cudaEventRecord(pe0, h->s_main));
 	}
 	int rc;
+	if (h->vc.on) {
+		MmaArgs ma;
+		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local; ma.tile = h->vc.tile;
+		ma.ntiles = h->vc.ntiles; ma.NWSG = h->vc.NWSG; ma.KW = h->vc.KW; ma.total_warps = h->vc.total_warps; ma.dynamic = h->vc.dynamic;
+		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = 0; ma.NT = 0; ma.invL = invL;
+		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+		rc = sqt_launch_vec(h->vc, ma, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_vec_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+	}
 	if (h->mc.on) {
 		MmaArgs ma;
 		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
@@ -424,6 +450,16 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
 	rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
 	rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.rho_cur = h->d_rho_cur; rr.invL0 = h->d_invL0; rr.invL = invL;
+	if (h->vc.on) {
+		MmaReduceArgs mr;
+		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = 0; mr.n_local = h->n_local; mr.KW = h->vc.KW; mr.NWSG = h->vc.NWSG;
+		mr.S = 0; mr.NT = h->vc.C + 2; mr.SPW = h->vc.SPW;
+		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
+		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
+		rc = sqt_launch_vec_reduce(mr, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "vec_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+	}
 	if (h->mc.on) {
 		MmaReduceArgs mr;
 		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = h->mc.SPOUT; mr.n_local = h->n_local; mr.KW = h->mc.KW; mr.NWSG = h->mc.NWSG; mr.S = h->mc.S; mr.NT = h->mc.NT; mr.SPW = h->mc.SPW;

@@ -65,6 +65,7 @@ struct MmaArgs {
 };
 struct MmaChoice {
 	int on;                   // 1: use the mma path for the real slots (the classic kernel then serves only rho)
+	int geo;                  // 1: S / NT / SPOUT are valid (the rho kernel can run) even if on == 0
 	int S, NT, SPW, SPOUT, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // SPW = origin slots per warp, SPOUT = MSD/MQD summed outside the product
 	size_t smem;
 };
@@ -80,6 +81,16 @@ struct MmaReduceArgs {
 	double invL;
 };
 int sqt_launch_mma_reduce(const MmaReduceArgs &a, cudaStream_t st);
+// ---- sqt_vec.cu: particle-per-lane kernel for small nCSpatial (<= 32); takes MmaArgs / MmaReduceArgs (NT = row width C + 2)
+struct VecChoice {
+	int on;
+	int C, SPW, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // C = nCSpatial rounded up to 4
+	size_t smem;
+};
+int sqt_pick_vec(int nCS, int B, int n_local, int n_sm, VecChoice *vc);
+int sqt_launch_vec(const VecChoice &vc, const MmaArgs &a, cudaStream_t st);
+int sqt_launch_vec_reduce(const MmaReduceArgs &a, cudaStream_t st);
+
 struct RhoMmaArgs {
 	const double *cur;        // current frame, SoA [3][cur_pitch]
 	double *partial;          // per-block fragments [block][axis][cos|sin][NT][32 lanes][2]
@@ -90,7 +101,7 @@ struct RhoMmaArgs {
 	double invL;
 };
 struct RhoMmaChoice { int on, blocks, WPB, total_warps, occ; size_t smem; };
-int sqt_pick_rho_mma(const MmaChoice &mc, int n_local, int n_sm, RhoMmaChoice *rc);
+int sqt_pick_rho_mma(const MmaChoice &mc, int n_local, int n_sm, RhoMmaChoice *rc); // needs only mc.S / NT / SPOUT (valid whenever mc.geo)
 int sqt_launch_rho_mma(const MmaChoice &mc, const RhoMmaChoice &rc, const RhoMmaArgs &a, cudaStream_t st);
 
 // ---- kernels.cu ---------------------------------------------------------------------------

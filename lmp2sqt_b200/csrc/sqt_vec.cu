@@ -1,0 +1,251 @@
+// sqt_vec.cu -- self terms for SMALL nCSpatial (<= 32: the shipped decks in.lmp2sqt.150 / .150.smallQ, BASELINE configs
+// 1 and 2) with a particle on every lane.
+//
+// At small nCSpatial neither the recurrence kernel of sqt_kernels.cu (a thread per origin slot: every lane pays the
+// ~57 FP64 instructions of displacement + three cos(2 pi u) for nCSpatial recurrence steps that are shorter than that,
+// one particle per warp iteration, 6 virtual rho slots on 32 lanes) nor the DMMA product of sqt_mma.cu (its shared-memory
+// staging costs more than nCSpatial multiply-adds) fits.  Here a warp owns SPW origin slots like the tensor-core kernel, a
+// LANE owns a particle, and the nCSpatial running sums of F_s live in the lane's registers:
+//     per (particle, origin, axis):  c = cos(2 pi u);  x_{m+1} = 2 c x_m - x_{m-1};  acc[m] += x_m      (lmp2sqt.c:1188-1196)
+// -- the reference's own recurrence, three independent chains per lane, all 32 lanes busy, origin positions read from
+// the particle-minor ring as one 256-byte access.  MSD, MQD and the van Hove bin are taken per (particle, origin) as in
+// the other kernels.  At the end the lane sums are combined by a fixed butterfly and one row per warp and slot is left
+// for vec_reduce_kernel.  rho(k) comes from rho_mma_kernel (sqt_mma.cu), which works at any nCSpatial.
+#include "sqt_internal.h"
+#include "sqt_lane.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+
+template <int C, int SPW, bool VARBOX>
+__global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_kernel(const MmaArgs a)
+{
+	extern __shared__ long long s_mem[];
+	const int wpb = blockDim.x >> 5;
+	const int SB = wpb * SPW;
+	long long *s_thr = s_mem;                          // [nCS + 2]
+	int *s_hist = (int *)(s_mem + a.nCS + 2);          // [SB][nCS]
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int gw = blockIdx.x * wpb + warp;
+	const int wsg = gw % a.NWSG, kq = gw / a.NWSG;
+	const int slot0 = wsg * SPW;
+	const int nCS = a.nCS;
+
+	for (int e = threadIdx.x; e < nCS * SB; e += blockDim.x) s_hist[e] = 0;
+	for (int e = threadIdx.x; e < nCS + 2; e += blockDim.x) s_thr[e] = a.thr[e];
+
+	unsigned live_m = 0, cap_m = 0;
+#pragma unroll
+	for (int s = 0; s < SPW; ++s) {
+		int tau = 0;
+		const bool lv = slot0 + s < a.B && mma_slot_state(slot0 + s, a.p, a.T, a.B, &tau);
+		if (lv) live_m |= 1u << s;
+		if (lv && tau == 0) cap_m |= 1u << s;
+	}
+	const double invL = a.invL;
+	double acc[SPW][C], msd[SPW], mqd[SPW];
+#pragma unroll
+	for (int s = 0; s < SPW; ++s) {
+		msd[s] = 0.0; mqd[s] = 0.0;
+#pragma unroll
+		for (int m = 0; m < C; ++m) acc[s][m] = 0.0;
+	}
+	__syncthreads();
+
+	const double *cx = a.cur, *cy = cx + a.cur_pitch, *cz = cy + a.cur_pitch;
+	const long long RP = a.RP;
+	const int nws = (a.total_warps - wsg + a.NWSG - 1) / a.NWSG;
+	int jgrab = 0;
+	auto grab = [&]() -> int {
+		int t;
+		if (a.dynamic) {
+			t = 0;
+			if (lane == 0) t = atomicAdd(&a.tile_ctr[wsg], 1);
+		} else {
+			t = kq + jgrab * nws;
+			++jgrab;
+		}
+		t = __reduce_max_sync(0xffffffffu, t);
+		return t < a.ntiles ? t : -1;
+	};
+
+	if (live_m) {
+		for (int tile = grab(); tile >= 0; tile = grab()) {
+			const int tbase = tile * a.tile;
+			int tlen = a.n_local - tbase;
+			tlen = tlen < a.tile ? tlen : a.tile;
+			for (int i0 = 0; i0 < tlen; i0 += 32) {
+				const bool valid = i0 + lane < tlen;
+				const long long n = tbase + (valid ? i0 + lane : tlen - 1);
+				const double rx = __ldg(cx + n), ry = __ldg(cy + n), rz = __ldg(cz + n);
+				double *rrow = a.ring + (long long)slot0 * 3 * RP + n; // [slot][axis][particle]
+#pragma unroll
+				for (int s = 0; s < SPW; ++s) {
+					if (!((live_m >> s) & 1)) continue;
+					const bool capture = (cap_m >> s) & 1;
+					double *rs = rrow + (long long)s * 3 * RP;
+					double ox, oy, oz;
+					if (capture) {
+						ox = rx; oy = ry; oz = rz;
+						if (valid) { rs[0] = rx; rs[RP] = ry; rs[2 * RP] = rz; } // SetWaitedTimeCorr, lmp2sqt.c:1279-1282
+					} else { ox = __ldg(rs); oy = __ldg(rs + RP); oz = __ldg(rs + 2 * RP); }
+					const double dx = rx - ox, dy = ry - oy, dz = rz - oz; // lmp2sqt.c:1407-1409
+					// un-fused like the reference's x86-64 build so that dr2, hence the bin, is bit-identical
+					const double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+					{
+						int bi = lane_vanhove_bin(dr2, a.inv_rVal, nCS, s_thr);
+						if (!valid) bi = nCS; // not counted
+						const unsigned peers = __match_any_sync(0xffffffffu, bi);
+						if (bi < nCS && lane == (__ffs(peers) - 1)) s_hist[(warp * SPW + s) * nCS + bi] += __popc(peers);
+					}
+					if (valid) { msd[s] += dr2; mqd[s] = fma(dr2, dr2, mqd[s]); }
+					double ux = dx * invL, uy = dy * invL, uz = dz * invL;
+					if (VARBOX && !capture) {
+						const double dsl = invL - a.invL0[slot0 + s];
+						ux = fma(ox, dsl, ux); uy = fma(oy, dsl, uy); uz = fma(oz, dsl, uz);
+					}
+					// three chains at once; an invalid lane runs them on zeros (x_0 = 0 keeps every x_m = 0)
+					const double c0 = mma_cos2pi(ux), c1 = mma_cos2pi(uy), c2 = mma_cos2pi(uz);
+					const double one = valid ? 1.0 : 0.0;
+					double p0 = one, p1 = one, p2 = one;                                  // x_0 = T_0
+					double x0 = valid ? c0 : 0.0, x1 = valid ? c1 : 0.0, x2 = valid ? c2 : 0.0; // x_1 = T_1
+					const double t0 = c0 + c0, t1 = c1 + c1, t2 = c2 + c2;
+#pragma unroll
+					for (int m = 0; m < C; ++m) {
+						acc[s][m] += (x0 + x1) + x2;
+						const double n0 = fma(t0, x0, -p0), n1 = fma(t1, x1, -p1), n2 = fma(t2, x2, -p2);
+						p0 = x0; p1 = x1; p2 = x2;
+						x0 = n0; x1 = n1; x2 = n2;
+					}
+				}
+			}
+		}
+	}
+
+	// lane sums -> warp sums by a fixed butterfly; partial rows [slot group][k-th warp][slot][C + 2]
+	if (kq < a.KW) {
+		double *pb = a.partial + ((long long)(wsg * a.KW + kq) * SPW) * (C + 2);
+#pragma unroll
+		for (int s = 0; s < SPW; ++s) {
+#pragma unroll
+			for (int m = 0; m < C + 2; ++m) {
+				double v = m < C ? acc[s][m < C ? m : 0] : (m == C ? msd[s] : mqd[s]);
+#pragma unroll
+				for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+				if (lane == (m & 31)) pb[s * (C + 2) + m] = v;
+			}
+		}
+	}
+	__syncthreads();
+	for (int e = threadIdx.x; e < nCS * SB; e += blockDim.x) {
+		const int cntv = s_hist[e];
+		if (cntv) {
+			const int col = e / nCS;
+			const int gwc = blockIdx.x * wpb + col / SPW;
+			const int sl = (gwc % a.NWSG) * SPW + col % SPW;
+			atomicAdd(&a.hist_cur[sl * nCS + e % nCS], cntv);
+		}
+	}
+}
+
+// one block per origin slot: fixed-order sum of the per-warp rows, scatter to the TBuf layout (F_s_qq2 / rrMSD / rrMQD /
+// DrTable), re-arm the histogram and the tile counters
+__global__ void vec_reduce_kernel(const MmaReduceArgs a)
+{
+	const int slot = blockIdx.x;
+	const int W = a.NT; // row width C + 2 (the field is reused)
+	int tau = 0;
+	const bool live = slot < a.B && mma_slot_state(slot, a.p, a.T, a.B, &tau);
+	if (slot < a.B) {
+		const int SPW = a.SPW, wsg = slot / SPW, s = slot % SPW;
+		if (live) {
+			for (int m = threadIdx.x; m < W; m += blockDim.x) {
+				const double *p = a.partial + ((long long)(wsg * a.KW) * SPW + s) * W + m;
+				const long long stride = (long long)SPW * W;
+				double v = 0.0;
+				for (int k = 0; k < a.KW; ++k) v += p[k * stride];
+				if (m < a.nCS) a.bufFs[((long long)slot * a.T + tau) * a.nCS + m] = v;
+				else if (m == W - 2) a.bufMSD[slot * a.T + tau] = v;
+				else if (m == W - 1) a.bufMQD[slot * a.T + tau] = v;
+			}
+			if (threadIdx.x == 0 && tau == 0) a.invL0[slot] = a.invL;
+			for (int bin = threadIdx.x; bin < a.nCS; bin += blockDim.x)
+				a.bufHist[((long long)slot * a.T + tau) * a.nCS + bin] = a.hist_cur[slot * a.nCS + bin];
+		}
+		__syncthreads();
+		for (int bin = threadIdx.x; bin < a.nCS; bin += blockDim.x) a.hist_cur[slot * a.nCS + bin] = 0;
+	}
+	if (slot == 0)
+		for (int i = threadIdx.x; i < a.NWSG; i += blockDim.x) a.tile_ctr[i] = 0;
+}
+
+typedef void (*vec_fn)(const MmaArgs);
+static vec_fn vec_variant(int C, int SPW, int varbox)
+{
+#define VV(C_, SPW_) if (C == C_ && SPW == SPW_) return varbox ? (vec_fn)self_ring_vec_kernel<C_, SPW_, true> : (vec_fn)self_ring_vec_kernel<C_, SPW_, false>;
+	VV(4, 2) VV(8, 2) VV(12, 2)
+	VV(16, 1) VV(20, 1) VV(24, 1) VV(28, 1) VV(32, 1)
+#undef VV
+	return nullptr;
+}
+
+static int vec_env_int(const char *name, int dflt)
+{
+	const char *s = getenv(name);
+	return (s && *s) ? atoi(s) : dflt;
+}
+
+int sqt_pick_vec(int nCS, int B, int n_local, int n_sm, VecChoice *vc)
+{
+	vc->on = 0;
+	const int want = vec_env_int("SQT_VEC", -1);
+	if (want == 0 || B < 1 || nCS < 1 || nCS > 32) return 0;
+	const int C = (nCS + 3) / 4 * 4;
+	const int SPW = C <= 12 ? 2 : 1; // 2 C SPW registers of running sums per lane
+	const int W = 4;
+	const size_t sm = sizeof(long long) * (nCS + 2) + sizeof(int) * (size_t)nCS * W * SPW;
+	for (int vb = 0; vb < 2; ++vb) {
+		cudaError_t e = cudaFuncSetAttribute((const void *)vec_variant(C, SPW, vb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+		if (e != cudaSuccess) return (int)e;
+	}
+	int occ = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)vec_variant(C, SPW, 0), W * 32, sm);
+	if (e != cudaSuccess) return (int)e;
+	if (occ < 1) return 0;
+	cudaFuncAttributes fa;
+	cudaFuncGetAttributes(&fa, (const void *)vec_variant(C, SPW, 0));
+	vc->C = C; vc->SPW = SPW; vc->WPB = W; vc->occ = occ; vc->regs = fa.numRegs; vc->smem = sm;
+	vc->NWSG = (B + SPW - 1) / SPW;
+	int blocks = n_sm * occ;
+	long long warps_per_group = ((long long)blocks * W + vc->NWSG - 1) / vc->NWSG;
+	long long ts = n_local / (4 * warps_per_group); // about 4 tiles per warp, a multiple of 32, 32 .. 256 particles
+	ts = (ts / 32) * 32;
+	if (ts < 32) ts = 32;
+	if (ts > 256) ts = 256;
+	const int fT = vec_env_int("SQT_TILE", 0);
+	if (fT > 0) ts = ((fT + 31) / 32) * 32;
+	vc->tile = (int)ts;
+	vc->ntiles = (int)((n_local + ts - 1) / ts);
+	long long need = (long long)vc->ntiles * vc->NWSG;
+	if ((long long)blocks * W > need) blocks = (int)((need + W - 1) / W);
+	if (blocks < 1) blocks = 1;
+	vc->blocks = blocks;
+	vc->total_warps = blocks * W;
+	vc->KW = (vc->total_warps + vc->NWSG - 1) / vc->NWSG;
+	vc->dynamic = vec_env_int("SQT_DETERMINISTIC", 0) ? 0 : 1;
+	vc->on = 1;
+	return 0;
+}
+
+int sqt_launch_vec(const VecChoice &vc, const MmaArgs &a, cudaStream_t st)
+{
+	vec_fn fn = vec_variant(vc.C, vc.SPW, a.varbox);
+	if (!fn) return -1;
+	fn<<<vc.blocks, vc.WPB * 32, vc.smem, st>>>(a);
+	return (int)cudaGetLastError();
+}
+
+int sqt_launch_vec_reduce(const MmaReduceArgs &a, cudaStream_t st)
+{
+	vec_reduce_kernel<<<a.B, 64, 0, st>>>(a);
+	return (int)cudaGetLastError();
+}
