@@ -54,3 +54,17 @@ __device__ __forceinline__ int lane_vanhove_bin(const double dr2, const float in
 	}
 	return bi;
 }
+
+// sum of n values p[0], p[stride], ... in a fixed order, four independent chains so that the loads overlap
+// (the reduce kernels are latency bound: one dependent L2 access per addend otherwise)
+__device__ __forceinline__ double strided_sum(const double *p, const long long stride, const int first, const int n, const int step)
+{
+	double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+	int k = first;
+	for (; k + 3 * step < n; k += 4 * step) {
+		v0 += p[(long long)k * stride]; v1 += p[(long long)(k + step) * stride];
+		v2 += p[(long long)(k + 2 * step) * stride]; v3 += p[(long long)(k + 3 * step) * stride];
+	}
+	for (; k < n; k += step) v0 += p[(long long)k * stride];
+	return (v0 + v1) + (v2 + v3);
+}

@@ -161,8 +161,7 @@ __global__ void vec_reduce_kernel(const MmaReduceArgs a)
 			for (int m = threadIdx.x; m < W; m += blockDim.x) {
 				const double *p = a.partial + ((long long)(wsg * a.KW) * SPW + s) * W + m;
 				const long long stride = (long long)SPW * W;
-				double v = 0.0;
-				for (int k = 0; k < a.KW; ++k) v += p[k * stride];
+				const double v = strided_sum(p, stride, 0, a.KW, 1);
 				if (m < a.nCS) a.bufFs[((long long)slot * a.T + tau) * a.nCS + m] = v;
 				else if (m == W - 2) a.bufMSD[slot * a.T + tau] = v;
 				else if (m == W - 1) a.bufMQD[slot * a.T + tau] = v;
