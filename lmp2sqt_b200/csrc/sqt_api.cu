@@ -429,7 +429,10 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
 	}
+	const bool split = h->s_coll != h->s_main;
 	if (h->rmc.on) { // rho(k) and sum_n r on the tensor-core path too: the classic kernel is not launched at all
+		// its reduce rewrites d_rho_cur, which the previous frame's allreduce + collective stage (other stream) still reads
+		if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
 		RhoMmaArgs qa;
 		qa.cur = h->d_cur[slot]; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT; qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
 		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.n_sets = h->rmc.blocks; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
@@ -444,7 +447,6 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	CU(cudaEventRecord(h->ev_ring[slot], h->s_main));
 	h->launches++;
 
-	const bool split = h->s_coll != h->s_main;
 	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0)); // previous frame's collective stage
 	ReduceArgs rr;
 	rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
