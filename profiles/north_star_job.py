@@ -28,6 +28,7 @@ N_CELLS, S, T, B, SIGMA = 159, 171, 150, 150, 0.077
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=5000)
+    ap.add_argument("--dump", default="", help="write rank 0's raw sums to this .npz (to compare runs on different GPU counts)")
     ap.add_argument("--cells", type=int, default=N_CELLS, help="fcc cells per edge (159 = the north-star 16 078 716 atoms)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -82,6 +83,8 @@ def main():
             "kernel": eng.kernel_config.split(";")[0],
         }
         print(json.dumps(line), flush=True)
+        if args.dump:
+            np.savez_compressed(args.dump, **{k: v for k, v in r.items() if isinstance(v, np.ndarray)}, countCorrAv=cnt)
     eng.close()
     src.close()
     if world > 1:
