@@ -231,6 +231,62 @@ static int tok_skip(const char **c, const char *e)
 	return 1;
 }
 
+/* Common-case line "<id> <type> <x> <y> <z>[ ...]\n": one forward scan, no token pre-scan, no bounds checks (the caller
+ * guarantees >= FAST_MARGIN readable bytes after p).  Numbers go through the same correctly rounded fast path as
+ * tok_real (<= 15 digits, one division).  Returns the start of the next line, or NULL when anything is unusual
+ * (exponent, long mantissa, tab, short line, ...): the caller then re-parses that line with the general code, so the
+ * semantics are those of the general code in every case. */
+#define FAST_MARGIN 512
+#define FAST_SCAN (FAST_MARGIN - 160) /* no loop below runs past line start + FAST_SCAN; the final memchr looks at most 128 further */
+static inline const char *fast_real(const char *p, const char *lim, double *out)
+{
+	static const double p10[19] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18 };
+	int neg = 0;
+	if (*p == '-') { neg = 1; p++; } else if (*p == '+') p++;
+	const char *d0 = p;
+	unsigned long long mant = 0;
+	unsigned d;
+	while ((d = (unsigned)(*p - '0')) <= 9 && p < lim) { mant = mant * 10 + d; p++; }
+	int nd = (int)(p - d0), scale = 0;
+	if (*p == '.') {
+		const char *f0 = ++p;
+		while ((d = (unsigned)(*p - '0')) <= 9 && p < lim) { mant = mant * 10 + d; p++; }
+		scale = (int)(p - f0);
+		nd += scale;
+	}
+	if (nd == 0 || nd > 15 || (*p != ' ' && *p != '\n' && *p != '\r')) return NULL; /* leading zeros count here: conservative */
+	const double v = (double)mant / p10[scale];
+	*out = neg ? -v : v;
+	return p;
+}
+
+static inline const char *fast_line(const char *p, double *x, double *y, double *z)
+{
+	const char *lim = p + FAST_SCAN;
+#define SKIP_SPACES while (*p == ' ' && p < lim) p++
+#define SKIP_DIGITS while ((unsigned)(*p - '0') <= 9 && p < lim) p++
+	SKIP_SPACES;
+	if ((unsigned)(*p - '0') > 9) return NULL;
+	SKIP_DIGITS;                                        /* id */
+	if (*p != ' ') return NULL;
+	SKIP_SPACES;
+	if ((unsigned)(*p - '0') > 9) return NULL;
+	SKIP_DIGITS;                                        /* type */
+	if (*p != ' ') return NULL;
+	SKIP_SPACES;
+	if (!(p = fast_real(p, lim, x)) || *p != ' ') return NULL;
+	SKIP_SPACES;
+	if (!(p = fast_real(p, lim, y)) || *p != ' ') return NULL;
+	SKIP_SPACES;
+	if (!(p = fast_real(p, lim, z))) return NULL;
+#undef SKIP_SPACES
+#undef SKIP_DIGITS
+	if (*p == '\n') return p + 1;
+	if (p >= lim) return NULL;
+	const char *nl = (const char *)memchr(p, '\n', 128); /* trailing columns (velocities, ...) or \r */
+	return nl ? nl + 1 : NULL;
+}
+
 sqt_reader *sqt_reader_open(const char *path, int n_threads)
 {
 	int fd = open(path, O_RDONLY);
@@ -371,6 +427,10 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 		const int i0 = t * step, i1 = (i0 + step < n) ? i0 + step : n;
 		size_t pos = starts[t];
 		for (int i = i0; i < i1; i++) {
+			if (r->size - pos > FAST_MARGIN) { /* far enough from the end of the mapping for the unchecked scan */
+				const char *nx = fast_line(r->base + pos, &x[i], &y[i], &z[i]);
+				if (nx) { pos = (size_t)(nx - r->base); continue; }
+			}
 			const char *p, *e;
 			if (!take_line(r, &pos, &p, &e)) { bad |= 2; break; }
 			int ok = 1;

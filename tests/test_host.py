@@ -312,3 +312,45 @@ def test_lammps_native_binary_rejects_what_the_text_reader_rejects(tmp_path):
     data = (tmp_path / "tri.bin").read_bytes()
     (tmp_path / "atom.bin").write_bytes(data.replace(b"DUMPCUSTOM", b"DUMPATOMXX"))
     assert _read_all_frames_mmap(str(tmp_path / "atom.bin"), 1) == []
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_mmap_reader_fast_and_general_line_paths_agree_with_strtod(tmp_path, threads):
+    """The single-scan fast path of the mmap reader takes plain decimal lines; everything else (exponents, long
+    mantissas, '+', CRLF, extra columns, a short last line, lines near the end of the mapping) must fall back to the
+    general path -- and every value must equal strtod's (Python float) whichever path parsed it."""
+    rng = np.random.default_rng(5)
+    n, frames = 2500, 3
+    txt, want = [], []
+    for f in range(frames):
+        txt += ["ITEM: TIMESTEP", str(f * 10), "ITEM: NUMBER OF ATOMS", str(n), "ITEM: BOX BOUNDS pp pp pp",
+                "0.000000 16.796000", "0.0 16.796", "0 16.796", "ITEM: ATOMS id type xu yu zu vx vy vz"]
+        rows = []
+        for i in range(n):
+            x, y, z = rng.normal(0, 50, 3)
+            kind = i % 9
+            if kind == 0:
+                s = ["%.6f" % x, "%.3e" % y, "%.6f" % z]                 # exponent -> general path
+            elif kind == 1:
+                s = ["%+.6f" % x, "%.6f" % y, "%.17g" % z]               # '+' sign, 17 significant digits
+            elif kind == 2:
+                s = ["%d" % int(x), "%.1f" % y, "-0.000001"]             # integers, tiny numbers
+            elif kind == 3:
+                s = ["%.6f" % x, " %.6f" % y, "%.6f" % z]                # double space between tokens
+            elif kind == 4:
+                s = ["000012.500", "%.6f" % y, "%.6f" % z]               # leading zeros
+            else:
+                s = ["%.6f" % x, "%.6f" % y, "%.6f" % z]
+            tail = " 0.100000 -0.200000 0.300000" + ("\r" if kind == 5 else "")
+            txt.append("%d 1 %s %s %s%s" % (i + 1, s[0], s[1], s[2], tail))
+            rows.append([float(v) for v in s])
+        want.append(np.array(rows))
+    p = tmp_path / "mixed.lammpstrj"
+    p.write_text("\n".join(txt))                                          # no trailing newline: the last line ends the mapping
+    got = _read_all_frames_mmap(str(p), threads)
+    assert len(got) == frames
+    for (ts, na, box, xyz), w in zip(got, want):
+        assert na == n and np.array_equal(xyz.T, w)
+    ref = _read_all_frames(str(p))                                        # the stream reader (sqt_dump.c) sees the same
+    for (a, b) in zip(got, ref):
+        assert np.array_equal(a[3], b[3])
