@@ -127,9 +127,10 @@ int  sqt_number_call_print(const sqt_handle *h);
 /* rho(k) of the last processed frame, [3][nCSpatial][2] (marker layout lmp2sqt.c:1173-1174). */
 int  sqt_get_rho(sqt_handle *h, double *out);
 long long sqt_kernel_launches(const sqt_handle *h);       /* launches of OUR kernels so far */
-/* CUDA-event timing of the dominant kernel (self_ring) on its own stream.  enable=1 starts
- * recording (one event pair per launch); sqt_profile_read synchronises and returns the count
- * and summed milliseconds since enable, then clears. */
+/* CUDA-event timing of a frame's dominant kernels on their own stream: the self-term kernel of the family in
+ * use (self_ring_mma_kernel / self_ring_vec_kernel / self_ring_kernel) plus the rho(k) kernel, one event pair around
+ * both per frame.  enable=1 starts recording; sqt_profile_read synchronises and returns the number of frames and
+ * the summed milliseconds since enable, then clears. */
 int  sqt_profile_enable(sqt_handle *h, int enable);
 int  sqt_profile_read(sqt_handle *h, long long *n_launches, double *ms_total);
 /* Device-side clock over a region of frames: start records an event on the engine's main
