@@ -318,7 +318,7 @@ def main():
     alg_bytes = n_local * 24.0 * (1 + B)             # current positions + B origin positions per particle
     cfg_now = eng.kernel_config
     on_mma = cfg_now.startswith("self_ring_mma_kernel")
-    family = "self_ring_mma_kernel" if on_mma else "self_ring_kernel"
+    family = "self_ring_mma_kernel" if on_mma else ("self_ring_vec_kernel" if cfg_now.startswith("self_ring_vec_kernel") else "self_ring_kernel")
     if on_mma:
         # what the tensor-core path executes instead of the recurrence: per (particle, origin, axis) an 8 x 8NT x 1 slice of
         # the blocked-Chebyshev product on DMMA (the share of the FP64 pipe those DMMAs occupy is dmma_pipe_frac)
@@ -328,7 +328,12 @@ def main():
                      "fp64_pipe_frac": None}
     else:
         pipe_note = {"fp64_pipe_frac": units_per_launch * (4 + 2 * B) / (ring_ms_avg * 1e-3) / (dfma_tf * 1e12 / 2.0)}
-    roofline = {"bound": "fp64_fma", "kernel": family + (" + rho_mma_kernel" if "rho_mma_kernel" in cfg_now else ""),
+    # "tensor" = the FP64 tensor-core (DMMA) path; it shares one pipe with vector DFMA and has the same measured peak
+    # (profiles/probes/dmma_probe.cu), so one denominator serves both kernel families
+    roofline = {"bound": "tensor" if on_mma else "fp64_fma",
+                "bound_detail": "FP64 pipe: DMMA m8n8k4 (tensor) and vector DFMA/DADD share it and have the same measured peak; "
+                                "HBM is at a few percent (roofline.hbm)",
+                "kernel": family + (" + rho_mma_kernel" if "rho_mma_kernel" in cfg_now else ""),
                 "achieved": ach_tf, "peak": dfma_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / dfma_tf, "traffic": None,
                 "peak_source": "measured live: register-resident DFMA microbenchmark (sqt_measure_dfma_peak), %.0f MHz implied" % dfma_mhz,
