@@ -354,3 +354,29 @@ def test_mmap_reader_fast_and_general_line_paths_agree_with_strtod(tmp_path, thr
     ref = _read_all_frames(str(p))                                        # the stream reader (sqt_dump.c) sees the same
     for (a, b) in zip(got, ref):
         assert np.array_equal(a[3], b[3])
+
+
+def test_mmap_reader_decimal_fast_path_is_correctly_rounded(tmp_path):
+    """20 000 random decimal strings (1..15 significant digits, 0..12 decimals, both signs, leading zeros): the reader's
+    one-division fast path must give exactly strtod's double for every one of them."""
+    rng = np.random.default_rng(99)
+    n = 20000
+    toks = []
+    for i in range(n * 3):
+        nd = int(rng.integers(1, 16))
+        digits = "".join(str(int(d)) for d in rng.integers(0, 10, nd))
+        dec = int(rng.integers(0, min(nd, 12) + 1))
+        s = digits[:nd - dec] + ("." + digits[nd - dec:] if dec else "")
+        if s.startswith("."):
+            s = "0" + s
+        if rng.random() < 0.1 and not s.startswith("-"):
+            s = "00" + s
+        toks.append(("-" if rng.random() < 0.5 else "") + s)
+    lines = ["ITEM: TIMESTEP", "0", "ITEM: NUMBER OF ATOMS", str(n), "ITEM: BOX BOUNDS pp pp pp", "0 1", "0 1", "0 1",
+             "ITEM: ATOMS id type xu yu zu"]
+    lines += ["%d 1 %s %s %s" % (i + 1, toks[3 * i], toks[3 * i + 1], toks[3 * i + 2]) for i in range(n)]
+    p = tmp_path / "dec.lammpstrj"
+    p.write_text("\n".join(lines) + "\n" + "x" * 600)      # padding: every atom line is far from the end of the mapping
+    (ts, na, box, xyz), = _read_all_frames_mmap(str(p), 2)
+    want = np.array([float(t) for t in toks]).reshape(n, 3)
+    assert np.array_equal(xyz.T, want)
