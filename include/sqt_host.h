@@ -59,7 +59,9 @@ int sqt_dump_read_atoms(FILE *fp, const sqt_frame_header *hd, double *x, double 
 int sqt_dump_skip_atoms(FILE *fp, const sqt_frame_header *hd);
 
 /* High-rate variant of the same reader: memory-mapped file, atom block parsed by n_threads threads (0 = auto,
- * SQT_READER_THREADS overrides) straight into the SoA staging buffer.  Same format rules and conversions. */
+ * SQT_READER_THREADS overrides; a thread is only added per SQT_READER_LINES_PER_THREAD = 131072 atom lines, smaller blocks are
+ * parsed by the caller alone) straight into the SoA staging buffer.  Same format rules and conversions.  A count pass
+ * (sqt_reader_skip_atoms over the file) indexes the atom blocks; after sqt_reader_rewind the parse pass reuses that index. */
 /* The same reader also accepts the raw binary frame file (an extension; the reference reads text only):
  *   "SQTRAW01", then per frame: int64 timestep, int64 n_atoms, f64 xlo xhi ylo yhi zlo zhi, f64 x[n], y[n], z[n]
  * (little endian, atoms in dump order).  It is recognised by its magic; sqt_raw_append_frame writes one frame. */

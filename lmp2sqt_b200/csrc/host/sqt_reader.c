@@ -27,10 +27,17 @@ struct sqt_reader {
 	const char *base;
 	size_t size, pos;
 	int fd, n_threads;
+	int lines_per_thread; /* least number of atom lines a thread must get before the parser forks (SQT_READER_LINES_PER_THREAD) */
 	int raw;          /* 0: LAMMPS text dump, 1: SQTRAW01 binary frame file (see sqt_host.h), 2: LAMMPS native binary dump */
 	/* LAMMPS binary: where the current frame's chunks start and how its rows are laid out */
 	size_t lb_chunks;
 	int lb_size_one, lb_nchunk, lb_col[3];
+	/* text dumps: what the count pass (sqt_reader_skip_atoms) learned about each atom block, so that the parse pass does
+	 * not scan for newlines again: block start / end and the start of every MARK_LINES-th line */
+	struct blk_index { size_t atoms_pos, end_pos; int n_atoms; size_t mark0; } *blk;
+	size_t n_blk, cap_blk, blk_cursor;
+	size_t *marks;
+	size_t n_marks, cap_marks;
 };
 
 /* Raw binary frame file (extension, SURVEY.md section 8f.1 "raw f64[3][N] frame file"):
@@ -237,6 +244,9 @@ static int tok_skip(const char **c, const char *e)
  * (exponent, long mantissa, tab, short line, ...): the caller then re-parses that line with the general code, so the
  * semantics are those of the general code in every case. */
 #define FAST_MARGIN 512
+#ifndef SQT_LINES_PER_THREAD
+#define SQT_LINES_PER_THREAD 131072
+#endif
 #define FAST_SCAN (FAST_MARGIN - 160) /* no loop below runs past line start + FAST_SCAN; the final memchr looks at most 128 further */
 static inline const char *fast_real(const char *p, const char *lim, double *out)
 {
@@ -312,6 +322,11 @@ sqt_reader *sqt_reader_open(const char *path, int n_threads)
 	n_threads = 1;
 #endif
 	r->n_threads = n_threads < 1 ? 1 : n_threads;
+	{
+		const char *env = getenv("SQT_READER_LINES_PER_THREAD");
+		r->lines_per_thread = env && *env ? atoi(env) : SQT_LINES_PER_THREAD;
+		if (r->lines_per_thread < 1) r->lines_per_thread = 1;
+	}
 	if (r->size >= 8 && memcmp(r->base, RAW_MAGIC, 8) == 0) { r->raw = 1; r->pos = 8; }
 	else if (r->size >= 8 && memcmp(r->base, "ITEM:", 5) != 0) r->raw = 2; /* neither text nor SQTRAW01: LAMMPS native binary */
 	return r;
@@ -320,12 +335,14 @@ sqt_reader *sqt_reader_open(const char *path, int n_threads)
 void sqt_reader_close(sqt_reader *r)
 {
 	if (!r) return;
+	free(r->blk);
+	free(r->marks);
 	if (r->base) munmap((void *)r->base, r->size);
 	close(r->fd);
 	free(r);
 }
 
-void sqt_reader_rewind(sqt_reader *r) { if (r) r->pos = r->raw == 1 ? 8 : 0; }
+void sqt_reader_rewind(sqt_reader *r) { if (r) { r->pos = r->raw == 1 ? 8 : 0; r->blk_cursor = 0; } }
 int sqt_reader_is_raw(const sqt_reader *r) { return r ? r->raw : 0; }
 
 int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd)
@@ -391,13 +408,92 @@ static int index_lines(const sqt_reader *r, int n, int step, size_t *starts, int
 	return 1;
 }
 
+#define MARK_LINES 1024
+#define SCAN_BLOCK 4096
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+static size_t count_nl(const char *p, size_t n)
+{
+	size_t c = 0, i = 0;
+	const __m128i nl = _mm_set1_epi8('\n'), zero = _mm_setzero_si128();
+	while (i + 16 <= n) { /* byte-wise match counters (at most 255 rounds before they could wrap), then one horizontal sum */
+		__m128i acc = zero;
+		for (int k = 0; k < 255 && i + 16 <= n; k++, i += 16)
+			acc = _mm_sub_epi8(acc, _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)(p + i)), nl));
+		const __m128i sum = _mm_sad_epu8(acc, zero);
+		c += (size_t)_mm_cvtsi128_si64(sum) + (size_t)_mm_cvtsi128_si64(_mm_srli_si128(sum, 8));
+	}
+	for (; i < n; i++) c += (p[i] == '\n');
+	return c;
+}
+#else
+static size_t count_nl(const char *p, size_t n)
+{
+	size_t c = 0;
+	for (size_t i = 0; i < n; i++) c += (p[i] == '\n');
+	return c;
+}
+#endif
+
+/* Newline scan of an n-line atom block in 4 KB steps (vector count; memchr only inside the steps that hold a wanted line
+ * start).  Records the start of every MARK_LINES-th line (optional) and the end of line n-1.  Same acceptance rule as
+ * index_lines: the last line may end with the file instead of a newline.  0 if the data ends early. */
+static int scan_block_lines(const sqt_reader *r, int n, size_t *marks, size_t *end_pos)
+{
+	size_t pos = r->pos, line = 0, next_mark = 0, k = 0;
+	while (line < (size_t)n) {
+		if (line == next_mark) { if (marks) marks[k] = pos; k++; next_mark += MARK_LINES; }
+		if (pos >= r->size) return 0;
+		const size_t target = next_mark < (size_t)n ? next_mark : (size_t)n; /* the next line start that is wanted */
+		const size_t blk = r->size - pos < SCAN_BLOCK ? r->size - pos : SCAN_BLOCK;
+		const size_t c = count_nl(r->base + pos, blk);
+		if (line + c < target) {
+			line += c; pos += blk;
+			if (pos >= r->size) { /* data exhausted: fine only if just the unterminated last line is left */
+				if (line == (size_t)n - 1 && r->base[r->size - 1] != '\n') { *end_pos = r->size; return 1; }
+				return 0;
+			}
+			continue;
+		}
+		size_t q = pos;
+		while (line < target) { /* the wanted start lies in this step: walk to it */
+			const char *nl = (const char *)memchr(r->base + q, '\n', pos + blk - q);
+			q = (size_t)(nl - r->base) + 1;
+			line++;
+		}
+		pos = q;
+	}
+	*end_pos = pos;
+	return 1;
+}
+
 int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd)
 {
-	size_t endp, dummy;
+	size_t endp;
 	if (hd->n_atoms <= 0) return 1;
 	if (r->raw == 2) return lb_walk_atoms(r, hd, NULL, NULL, NULL);
 	if (r->raw) { r->pos += (size_t)hd->n_atoms * 24; return 1; }
-	if (!index_lines(r, hd->n_atoms, hd->n_atoms, &dummy, 1, &endp)) { r->pos = r->size; return 0; }
+	const int n = hd->n_atoms;
+	const size_t nm = ((size_t)n + MARK_LINES - 1) / MARK_LINES;
+	if (r->n_marks + nm > r->cap_marks) {
+		size_t cap = r->cap_marks ? r->cap_marks * 2 : 4096;
+		while (cap < r->n_marks + nm) cap *= 2;
+		size_t *m = (size_t *)realloc(r->marks, cap * sizeof(size_t));
+		if (m) { r->marks = m; r->cap_marks = cap; }
+	}
+	if (r->n_blk == r->cap_blk) {
+		size_t cap = r->cap_blk ? r->cap_blk * 2 : 1024;
+		struct blk_index *b = (struct blk_index *)realloc(r->blk, cap * sizeof(*b));
+		if (b) { r->blk = b; r->cap_blk = cap; }
+	}
+	const int can_index = r->n_marks + nm <= r->cap_marks && r->n_blk < r->cap_blk;
+	if (!scan_block_lines(r, n, can_index ? r->marks + r->n_marks : NULL, &endp)) { r->pos = r->size; return 0; }
+	if (can_index) {
+		struct blk_index *b = &r->blk[r->n_blk++];
+		b->atoms_pos = r->pos; b->end_pos = endp; b->n_atoms = n; b->mark0 = r->n_marks;
+		r->n_marks += nm;
+	}
 	r->pos = endp;
 	return 1;
 }
@@ -413,19 +509,36 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 		r->pos += (size_t)n * 24;
 		return 1;
 	}
+	/* Threads only pay off on big blocks: a parallel region costs a wake-up of the workers, which sleep between frames
+	 * while the caller drives the GPU -- measured at 2 ms and more per region in CPU-quota'd containers (and far worse when
+	 * the OpenMP runtime spins instead), against 1 ms to parse 32 000 lines on one thread.  At least SQT_LINES_PER_THREAD
+	 * lines per thread, so a frame below that is parsed by the calling thread alone. */
 	int T = r->n_threads;
-	if (T > n / 2048 + 1) T = n / 2048 + 1; /* threads only pay off on big blocks */
+	if (T > n / r->lines_per_thread) T = n / r->lines_per_thread;
+	if (T < 1) T = 1;
 	const int step = (n + T - 1) / T;
 	size_t starts[64], endp;
 	if (T > 64) T = 64;
-	if (!index_lines(r, n, step, starts, T, &endp)) { r->pos = r->size; return 0; }
+	const struct blk_index *bi = NULL; /* indexed by the count pass? (blocks are visited in file order) */
+	while (r->blk_cursor < r->n_blk && r->blk[r->blk_cursor].atoms_pos < r->pos) r->blk_cursor++;
+	if (r->blk_cursor < r->n_blk && r->blk[r->blk_cursor].atoms_pos == r->pos && r->blk[r->blk_cursor].n_atoms == n) bi = &r->blk[r->blk_cursor];
+	if (bi) endp = bi->end_pos;
+	else if (!index_lines(r, n, step, starts, T, &endp)) { r->pos = r->size; return 0; }
 	int bad = 0;
 #ifdef _OPENMP
-#pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : bad)
+#pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : bad) if (T > 1)
 #endif
 	for (int t = 0; t < T; t++) {
 		const int i0 = t * step, i1 = (i0 + step < n) ? i0 + step : n;
-		size_t pos = starts[t];
+		if (i0 >= i1) continue;
+		size_t pos;
+		if (bi) { /* nearest recorded line start, then forward over at most MARK_LINES - 1 lines */
+			pos = r->marks[bi->mark0 + (size_t)i0 / MARK_LINES];
+			for (int skip = i0 % MARK_LINES; skip > 0; skip--) {
+				const char *nl = (const char *)memchr(r->base + pos, '\n', r->size - pos);
+				pos = nl ? (size_t)(nl - r->base) + 1 : r->size;
+			}
+		} else pos = starts[t];
 		for (int i = i0; i < i1; i++) {
 			if (r->size - pos > FAST_MARGIN) { /* far enough from the end of the mapping for the unchecked scan */
 				const char *nx = fast_line(r->base + pos, &x[i], &y[i], &z[i]);

@@ -188,6 +188,13 @@ def test_factor_dr_matches_oracle():
     assert np.array_equal(fd, o.factorDr())
 
 
+@pytest.fixture(autouse=True)
+def _threaded_parser_for_small_test_frames(monkeypatch):
+    """The reader forks its parser only above 131 072 lines per thread; the test frames are small, so lower the bar to
+    keep the threaded path under test."""
+    monkeypatch.setenv("SQT_READER_LINES_PER_THREAD", "1000")
+
+
 def _read_all_frames_mmap(path, threads):
     h = _lib.host_lib()
     r = h.sqt_reader_open(path.encode(), threads)
@@ -380,3 +387,48 @@ def test_mmap_reader_decimal_fast_path_is_correctly_rounded(tmp_path):
     (ts, na, box, xyz), = _read_all_frames_mmap(str(p), 2)
     want = np.array([float(t) for t in toks]).reshape(n, 3)
     assert np.array_equal(xyz.T, want)
+
+
+def _read_all_frames_mmap_two_pass(path, threads):
+    """What the command-line driver does: a count pass (sqt_reader_skip_atoms, which indexes the atom blocks), rewind,
+    then the parse pass on the same reader."""
+    h = _lib.host_lib()
+    r = h.sqt_reader_open(path.encode(), threads)
+    assert r
+    hd = SqtFrameHeader()
+    n_frames = 0
+    while h.sqt_reader_next_header(r, C.byref(hd)) and h.sqt_reader_skip_atoms(r, C.byref(hd)):
+        n_frames += 1
+    h.sqt_reader_rewind(r)
+    frames = []
+    for _ in range(n_frames):
+        assert h.sqt_reader_next_header(r, C.byref(hd))
+        xyz = np.empty((3, hd.n_atoms))
+        assert h.sqt_reader_read_atoms(r, C.byref(hd), xyz[0].ctypes.data, xyz[1].ctypes.data, xyz[2].ctypes.data)
+        frames.append((hd.timestep, hd.n_atoms, (hd.xlo, hd.xhi, hd.ylo, hd.yhi, hd.zlo, hd.zhi), xyz.copy()))
+    h.sqt_reader_close(r)
+    return frames
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+@pytest.mark.parametrize("trailing_newline", [True, False])
+def test_mmap_reader_indexed_parse_pass_equals_plain_parse(tmp_path, threads, trailing_newline):
+    """The count pass records the start of every 1024-th line of an atom block; the parse pass then starts its threads
+    from those marks instead of scanning for newlines again.  Same frames either way, for blocks that are not a multiple of
+    the mark spacing, for an unterminated last line, and for a truncated file (the incomplete frame is not counted)."""
+    t = synth.make_trajectory(n_cells=11, n_atoms=5123, n_frames=3, seed=21, box_jitter=0.01)
+    p = tmp_path / "d.lammpstrj"
+    synth.write_text_dump(t, str(p))
+    if not trailing_newline:
+        p.write_bytes(p.read_bytes()[:-1])
+    a = _read_all_frames_mmap(str(p), threads)
+    b = _read_all_frames_mmap_two_pass(str(p), threads)
+    c = _read_all_frames(str(p))
+    assert len(a) == len(b) == len(c) == 3
+    for fa, fb, fc in zip(a, b, c):
+        assert fa[:3] == fb[:3] == fc[:3]
+        assert np.array_equal(fa[3], fb[3]) and np.array_equal(fa[3], fc[3])
+        assert np.array_equal(fa[3].T, t.positions[a.index(fa)])
+    cut = tmp_path / "cut.lammpstrj"
+    cut.write_bytes(p.read_bytes()[:-4000])
+    assert len(_read_all_frames_mmap_two_pass(str(cut), threads)) == 2
