@@ -42,6 +42,7 @@ class Trajectory:
     box: np.ndarray
     timesteps: np.ndarray
     types: np.ndarray
+    velocities: np.ndarray | None = None   # [f, n, 3]; only dumps written with ``velocities=True`` carry them
 
     @property
     def n_frames(self) -> int:
@@ -101,10 +102,17 @@ def make_trajectory(
     else:
         Ls = np.full(n_frames, L)
     box[:, :, 1] = Ls[:, None]
+    # velocities: an Ornstein-Uhlenbeck-like sequence per particle (unit variance, correlation 0.8 per frame), independent
+    # of the positions' walk -- only their statistics matter to the -V correlators' tests
+    vel = np.empty_like(pos)
+    vel[0] = rng.normal(0.0, 1.0, size=(n, 3))
+    for f in range(1, n_frames):
+        vel[f] = 0.8 * vel[f - 1] + 0.6 * rng.normal(0.0, 1.0, size=(n, 3))
     if round_decimals is not None:
         pos = np.round(pos, round_decimals)
         box = np.round(box, round_decimals)
-    return Trajectory(pos, box, np.arange(n_frames, dtype=np.int64) * 100, np.ones(n, dtype=np.int32))
+        vel = np.round(vel, round_decimals)
+    return Trajectory(pos, box, np.arange(n_frames, dtype=np.int64) * 100, np.ones(n, dtype=np.int32), vel)
 
 
 def static_trajectory(n_cells: int, n_frames: int, seed: int = DEFAULT_SEED) -> Trajectory:
@@ -140,8 +148,9 @@ def cubic_lattice_trajectory(n_side: int, n_frames: int, a: float = 1.0) -> Traj
     return Trajectory(pos, box, np.arange(n_frames, dtype=np.int64), np.ones(len(p0), dtype=np.int32))
 
 
-def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None) -> None:
-    """Write ``traj`` as a LAMMPS text dump (``%.6f`` coordinates, ids 1..N in fixed order)."""
+def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None, velocities: bool = False) -> None:
+    """Write ``traj`` as a LAMMPS text dump (``%.6f`` coordinates, ids 1..N in fixed order); ``velocities`` adds the
+    ``vx vy vz`` columns (the reference's second accepted header, snapshot.c:296-331)."""
     own = isinstance(path_or_file, (str, os.PathLike))
     f = open(path_or_file, "w") if own else path_or_file
     try:
@@ -153,10 +162,13 @@ def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None)
             f.write("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % (traj.timesteps[fi], n))
             for a in range(3):
                 f.write("%.6f %.6f\n" % (b[a, 0], b[a, 1]))
-            f.write("ITEM: ATOMS id type xu yu zu\n")
+            f.write("ITEM: ATOMS id type xu yu zu vx vy vz\n" if velocities else "ITEM: ATOMS id type xu yu zu\n")
             buf = io.StringIO()
             p = traj.positions[fi]
-            np.savetxt(buf, np.column_stack([ids, traj.types, p]), fmt="%d %d %.6f %.6f %.6f")
+            if velocities:
+                np.savetxt(buf, np.column_stack([ids, traj.types, p, traj.velocities[fi]]), fmt="%d %d %.6f %.6f %.6f %.6f %.6f %.6f")
+            else:
+                np.savetxt(buf, np.column_stack([ids, traj.types, p]), fmt="%d %d %.6f %.6f %.6f")
             f.write(buf.getvalue())
     finally:
         if own:

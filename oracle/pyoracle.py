@@ -32,6 +32,9 @@ REF_ANALYSIS_BIN = os.path.join(HERE, "_ref", "analysis_binary_ref.out")
 
 NAMES2D = ["avF", "StdDevF", "avF_s", "StdDevF_s", "avF_d", "StdDevF_d", "avDrTable"]
 NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv"]
+# -V (flag_velocity) adds these (oracle array indices 7..9 and 3..4)
+NAMES2D_V = ["avC2_v_rho", "avC2_rho_v", "avC2_v_v"]
+NAMES1D_V = ["rrCvvAv", "rrCvcmvcmAv"]
 
 
 def build(force: bool = False) -> None:
@@ -49,14 +52,14 @@ def have_reference() -> bool:
 class _Params(C.Structure):
     _fields_ = [("kVal", C.c_double), ("deltaT", C.c_double), ("mass", C.c_double), ("rVal", C.c_double),
                 ("limitCorrAv", C.c_int), ("nCBuffer", C.c_int), ("nCSpatial", C.c_int), ("nCTime", C.c_int),
-                ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int)]
+                ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int), ("flag_V", C.c_int)]
 
 
 class OraclePort:
     """The plain-C restatement.  Method names follow the reference's call seam."""
 
     def __init__(self, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=0, deltaT=0.06,
-                 kVal=0.0981748, mass=1.0, flag_f=True, flag_F=True, flag_t=True):
+                 kVal=0.0981748, mass=1.0, flag_f=True, flag_F=True, flag_t=True, flag_V=False):
         build()
         L = C.CDLL(PORT_SO)
         L.sqt_oracle_create.restype = C.c_void_p
@@ -65,6 +68,7 @@ class OraclePort:
             getattr(L, fn).argtypes = [C.c_void_p]
             getattr(L, fn).restype = None
         L.sqt_oracle_push_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.sqt_oracle_push_frame_v.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.sqt_oracle_finish.argtypes = [C.c_void_p]
         L.sqt_oracle_set_limit.argtypes = [C.c_void_p, C.c_int]
         L.sqt_oracle_set_limit.restype = None
@@ -92,8 +96,11 @@ class OraclePort:
         self.S, self.T = nCSpatial, nCTime
         self.B = max(1, min(nCBuffer, nCTime))
         p = _Params(kVal, deltaT, mass, rVal, limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip,
-                    int(flag_f), int(flag_F), int(flag_t))
+                    int(flag_f), int(flag_F), int(flag_t), int(flag_V))
         self.h = L.sqt_oracle_create(C.byref(p))
+        self.flag_V = bool(flag_V)
+        self.names2d = NAMES2D + (NAMES2D_V if flag_V else [])
+        self.names1d = NAMES1D + (NAMES1D_V if flag_V else [])
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -103,9 +110,13 @@ class OraclePort:
     def begin_file(self):
         self.L.sqt_oracle_begin_file(self.h)
 
-    def push_frame(self, xyz: np.ndarray, xlo: float, xhi: float) -> int:
+    def push_frame(self, xyz: np.ndarray, xlo: float, xhi: float, vel: np.ndarray | None = None) -> int:
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
-        rc = self.L.sqt_oracle_push_frame(self.h, xyz.ctypes.data, xyz.shape[0], float(xlo), float(xhi))
+        if vel is not None:
+            vel = np.ascontiguousarray(vel, dtype=np.float64)
+            rc = self.L.sqt_oracle_push_frame_v(self.h, xyz.ctypes.data, vel.ctypes.data, xyz.shape[0], float(xlo), float(xhi))
+        else:
+            rc = self.L.sqt_oracle_push_frame(self.h, xyz.ctypes.data, xyz.shape[0], float(xlo), float(xhi))
         if rc < 0:
             raise RuntimeError("oracle push_frame failed rc=%d" % rc)
         return rc
@@ -136,22 +147,22 @@ class OraclePort:
         return np.ctypeslib.as_array(p, shape=shape).copy()
 
     def raw(self) -> dict:
-        d = {n: self._arr("raw2d", i, (self.S, self.T)) for i, n in enumerate(NAMES2D)}
-        d.update({n: self._arr("raw1d", i, (self.T,)) for i, n in enumerate(NAMES1D)})
+        d = {n: self._arr("raw2d", i, (self.S, self.T)) for i, n in enumerate(self.names2d)}
+        d.update({n: self._arr("raw1d", i, (self.T,)) for i, n in enumerate(self.names1d)})
         d["countCorrAv"] = self.countCorrAv
         return d
 
     def printed(self) -> dict:
-        d = {n: self._arr("printed2d", i, (self.S, self.T)) for i, n in enumerate(NAMES2D)}
-        d.update({n: self._arr("printed1d", i, (self.T,)) for i, n in enumerate(NAMES1D)})
+        d = {n: self._arr("printed2d", i, (self.S, self.T)) for i, n in enumerate(self.names2d)}
+        d.update({n: self._arr("printed1d", i, (self.T,)) for i, n in enumerate(self.names1d)})
         d["countCorrAv"] = self.printed_count
         d["kVal"] = self.kVal
         return d
 
     def printed_raw(self) -> dict:
         """Raw sums at the moment of the last print + the scalars the host normalisation needs."""
-        d = {n: self._arr("printed_raw2d", i, (self.S, self.T)) for i, n in enumerate(NAMES2D)}
-        d.update({n: self._arr("printed_raw1d", i, (self.T,)) for i, n in enumerate(NAMES1D)})
+        d = {n: self._arr("printed_raw2d", i, (self.S, self.T)) for i, n in enumerate(self.names2d)}
+        d.update({n: self._arr("printed_raw1d", i, (self.T,)) for i, n in enumerate(self.names1d)})
         d.update(countCorrAv=self.printed_count, kVal=self.kVal, nPtls=self.L.sqt_oracle_nPtls(self.h),
                  first_Vol=self.L.sqt_oracle_first_vol(self.h), first_limitCorrAv=self.L.sqt_oracle_first_limit(self.h),
                  g_Vol=self.L.sqt_oracle_vol(self.h), limitCorrAv=self.L.sqt_oracle_limitCorrAv(self.h))
@@ -173,7 +184,8 @@ def run_port(traj, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=
     flag_F = "F" in flags
     flag_f = flag_F or "f" in flags
     flag_t = "t" in flags
-    o = OraclePort(nCSpatial, nCTime, nCBuffer, nCSkip, rVal, 0, flag_f=flag_f, flag_F=flag_F, flag_t=flag_t)
+    flag_V = "V" in flags
+    o = OraclePort(nCSpatial, nCTime, nCBuffer, nCSkip, rVal, 0, flag_f=flag_f, flag_F=flag_F, flag_t=flag_t, flag_V=flag_V)
     limit = limitCorrAv
     B = min(nCBuffer, nCTime)
     use = []
@@ -192,7 +204,7 @@ def run_port(traj, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=
             continue
         o.begin_file()
         for f in range(t.n_frames):
-            rc = o.push_frame(t.positions[f], t.box[f, 0, 0], t.box[f, 0, 1])
+            rc = o.push_frame(t.positions[f], t.box[f, 0, 0], t.box[f, 0, 1], vel=t.velocities[f] if flag_V else None)
             log.append((o.countCorrAv, tuple(o.buffer_counts())))
             if rc == 1:
                 printed = o.printed()
@@ -251,6 +263,8 @@ class ReferenceLib:
         g("flag_F", C.c_bool).value = flag_F
         g("flag_f", C.c_bool).value = flag_F or ("f" in flags)
         g("flag_t", C.c_bool).value = "t" in flags
+        self.flag_V = "V" in flags
+        g("flag_velocity", C.c_bool).value = self.flag_V
         self.S, self.T, self.B = nCSpatial, nCTime, max(1, min(nCBuffer, nCTime))
         self.cl = _MakeSqtClass()
         C.c_void_p.in_dll(L, "classSqt").value = C.addressof(self.cl)
@@ -266,13 +280,15 @@ class ReferenceLib:
     def begin_file(self):
         self.L.InitSpacetimeCorr(C.byref(self.cl))
 
-    def push_frame(self, xyz: np.ndarray, xlo, xhi, box_yz=None) -> float:
-        """EvalSpacetimeCorr on a Snapshot built from ``xyz``; returns the call's wall seconds."""
+    def push_frame(self, xyz: np.ndarray, xlo, xhi, box_yz=None, vel=None) -> float:
+        """EvalSpacetimeCorr on a Snapshot built from ``xyz`` (and ``vel``); returns the call's wall seconds."""
         n = xyz.shape[0]
         atoms = np.zeros(n, dtype=ATOM_DTYPE)
         atoms["id"] = np.arange(1, n + 1)
         atoms["type"] = 1
         atoms["x"], atoms["y"], atoms["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        if vel is not None:
+            atoms["vx"], atoms["vy"], atoms["vz"] = vel[:, 0], vel[:, 1], vel[:, 2]
         snap = _Snapshot()
         snap.timestep = 0
         snap.NumAtoms = n
@@ -308,8 +324,10 @@ class ReferenceLib:
     def arrays(self) -> dict:
         m = {"avF": "avF_qq2", "StdDevF": "StdDevF_qq2", "avF_s": "avF_s_qq2", "StdDevF_s": "StdDevF_s_qq2",
              "avF_d": "avF_d_qq2", "StdDevF_d": "StdDevF_d_qq2", "avDrTable": "avDrTable"}
+        if self.flag_V:
+            m.update({k: k for k in NAMES2D_V})
         d = {k: self._a2(v) for k, v in m.items()}
-        for n in NAMES1D:
+        for n in NAMES1D + (NAMES1D_V if self.flag_V else []):
             d[n] = self._a1(n)
         d["countCorrAv"] = self.countCorrAv
         d["kVal"] = self._g("kVal", C.c_double).value
@@ -327,10 +345,10 @@ def _ref_worker(job_path: str) -> None:
     ref = ReferenceLib(**job["params"])
     ref.set_limit(job["limit"])
     times, log = [], []
-    for pos, box in job["files"]:
+    for pos, box, vel in job["files"]:
         ref.begin_file()
         for fi in range(pos.shape[0]):
-            dt = ref.push_frame(pos[fi], box[fi, 0, 0], box[fi, 0, 1])
+            dt = ref.push_frame(pos[fi], box[fi, 0, 0], box[fi, 0, 1], vel=None if vel is None else vel[fi])
             times.append(dt)
             log.append(ref.countCorrAv)
     raw = ref.arrays()
@@ -354,7 +372,7 @@ def run_reference(trajs, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, flags=
     with tempfile.TemporaryDirectory() as td:
         job = {"cwd": td, "out": os.path.join(td, "out.pkl"), "limit": int(limit), "normalise": normalise,
                "params": dict(nCSpatial=nCSpatial, nCTime=nCTime, nCBuffer=nCBuffer, nCSkip=nCSkip, rVal=rVal, flags=flags),
-               "files": [(t.positions, t.box) for t in trajs]}
+               "files": [(t.positions, t.box, t.velocities if "V" in flags else None) for t in trajs]}
         jp = os.path.join(td, "job.pkl")
         with open(jp, "wb") as f:
             pickle.dump(job, f)

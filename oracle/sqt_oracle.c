@@ -24,6 +24,8 @@
 #endif
 
 #define NAX 3 /* N_AXIS, lmp2sqt.h:103 */
+#define N2D 10
+#define N1D 5
 
 typedef struct {
 	/* per-origin copies, SetWaitedTimeCorr lmp2sqt.c:1260-1314 */
@@ -35,6 +37,11 @@ typedef struct {
 	double *F, *Fs, *Fd; /* [nCS][T] */
 	int *hist;           /* [nCS][T]  DrTable */
 	double *msd, *mqd, *msdcm; /* [T] */
+	/* -V (flag_velocity): origin velocities and current density, their correlators (lmp2sqt.h:49-71) */
+	double *org_vel;   /* [N][3]      orgV          */
+	double *org_kvel;  /* [6 nCS]     org_kvel_q1   */
+	double *Cvrho, *Crhov, *Cvv2; /* [nCS][T]  C2_v_rho, C2_rho_v, C2_v_v */
+	double *cvv, *cvcm;           /* [T]       rrCvv, rrCvcmvcm */
 	int count;
 } ring_buf;
 
@@ -48,10 +55,11 @@ struct sqt_oracle {
 	ring_buf *buf;
 	/* current frame (tBuf[0] scratch in the reference, lmp2sqt.c:1098-1102) */
 	double *rho, *tmp_row, *self, *dist;
-	const double *cur_xyz;
-	/* running sums: 0 avF 1 StdDevF 2 avF_s 3 StdDevF_s 4 avF_d 5 StdDevF_d 6 avDrTable */
-	double *sum2d[7], *out2d[7], *rawp2d[7]; /* running sums, normalised at last print, raw at last print */
-	double *sum1d[3], *out1d[3], *rawp1d[3]; /* 0 MSD 1 MQD 2 MSDCM */
+	double *kvel;      /* [6 nCS] kvel_q1: sum_n (q v_a) (-sin, cos)(q r_a), lmp2sqt.c:1203-1208 */
+	const double *cur_xyz, *cur_vel;
+	/* running sums: 0 avF 1 StdDevF 2 avF_s 3 StdDevF_s 4 avF_d 5 StdDevF_d 6 avDrTable 7 avC2_v_rho 8 avC2_rho_v 9 avC2_v_v */
+	double *sum2d[N2D], *out2d[N2D], *rawp2d[N2D]; /* running sums, normalised at last print, raw at last print */
+	double *sum1d[N1D], *out1d[N1D], *rawp1d[N1D]; /* 0 MSD 1 MQD 2 MSDCM 3 Cvv 4 Cvcmvcm */
 	double first_vol; int first_limit;
 	double *factorDr;
 };
@@ -75,10 +83,14 @@ sqt_oracle *sqt_oracle_create(const sqt_oracle_params *p)
 		b->hist = (int *)calloc((size_t)S * T, sizeof(int));
 		b->msd = zalloc(T); b->mqd = zalloc(T); b->msdcm = zalloc(T);
 		b->org_rho = zalloc(2 * NAX * S);
+		b->org_kvel = zalloc(2 * NAX * S);
+		b->Cvrho = zalloc((size_t)S * T); b->Crhov = zalloc((size_t)S * T); b->Cvv2 = zalloc((size_t)S * T);
+		b->cvv = zalloc(T); b->cvcm = zalloc(T);
 	}
-	for (int i = 0; i < 7; i++) { o->sum2d[i] = zalloc((size_t)S * T); o->out2d[i] = zalloc((size_t)S * T); o->rawp2d[i] = zalloc((size_t)S * T); }
-	for (int i = 0; i < 3; i++) { o->sum1d[i] = zalloc(T); o->out1d[i] = zalloc(T); o->rawp1d[i] = zalloc(T); }
+	for (int i = 0; i < N2D; i++) { o->sum2d[i] = zalloc((size_t)S * T); o->out2d[i] = zalloc((size_t)S * T); o->rawp2d[i] = zalloc((size_t)S * T); }
+	for (int i = 0; i < N1D; i++) { o->sum1d[i] = zalloc(T); o->out1d[i] = zalloc(T); o->rawp1d[i] = zalloc(T); }
 	o->rho = zalloc(2 * NAX * S);
+	o->kvel = zalloc(2 * NAX * S);
 	o->tmp_row = zalloc(2 * NAX * S);
 	o->factorDr = zalloc(S);
 	return o;
@@ -91,11 +103,12 @@ void sqt_oracle_destroy(sqt_oracle *o)
 		ring_buf *b = &o->buf[nb];
 		free(b->F); free(b->Fs); free(b->Fd); free(b->hist); free(b->msd); free(b->mqd);
 		free(b->msdcm); free(b->org_rho); free(b->org_pos); free(b->org_self); free(b->org_dist);
+		free(b->org_vel); free(b->org_kvel); free(b->Cvrho); free(b->Crhov); free(b->Cvv2); free(b->cvv); free(b->cvcm);
 	}
 	free(o->buf);
-	for (int i = 0; i < 7; i++) { free(o->sum2d[i]); free(o->out2d[i]); free(o->rawp2d[i]); }
-	for (int i = 0; i < 3; i++) { free(o->sum1d[i]); free(o->out1d[i]); free(o->rawp1d[i]); }
-	free(o->rho); free(o->tmp_row); free(o->self); free(o->dist); free(o->factorDr);
+	for (int i = 0; i < N2D; i++) { free(o->sum2d[i]); free(o->out2d[i]); free(o->rawp2d[i]); }
+	for (int i = 0; i < N1D; i++) { free(o->sum1d[i]); free(o->out1d[i]); free(o->rawp1d[i]); }
+	free(o->rho); free(o->kvel); free(o->tmp_row); free(o->self); free(o->dist); free(o->factorDr);
 	free(o);
 }
 
@@ -120,6 +133,7 @@ static void alloc_more(sqt_oracle *o)
 	o->dist = zalloc(N * row);
 	for (int nb = 0; nb < B; nb++) {
 		o->buf[nb].org_pos = zalloc((size_t)N * 3);
+		o->buf[nb].org_vel = zalloc((size_t)N * 3);
 		o->buf[nb].org_self = zalloc(N * row);
 		o->buf[nb].org_dist = zalloc(N * row);
 	}
@@ -138,7 +152,7 @@ static void one_time_kspace(sqt_oracle *o)
 	const int S = o->p.nCSpatial, N = o->N;
 	const int row = 2 * NAX * S;
 	const double kVal = o->kVal;
-	for (int j = 0; j < row; j++) o->rho[j] = 0.;
+	for (int j = 0; j < row; j++) { o->rho[j] = 0.; if (o->p.flag_V) o->kvel[j] = 0.; }
 	if (o->p.flag_F) {
 		memset(o->self, 0, sizeof(double) * (size_t)N * row);
 		memset(o->dist, 0, sizeof(double) * (size_t)N * row);
@@ -164,6 +178,12 @@ static void one_time_kspace(sqt_oracle *o)
 					c = 2. * c0 * c1 - c2;
 					s = 2. * c0 * s1 - s2;
 				}
+				if (o->p.flag_V) { /* :1203-1208 */
+					const int qn = m + 1;
+					const double kv = qn * kVal * o->cur_vel[3 * (size_t)n + k];
+					o->kvel[mR] += -kv * s;
+					o->kvel[mI] += +kv * c;
+				}
 				o->tmp_row[mR] = c;
 				o->tmp_row[mI] = s;
 			}
@@ -183,8 +203,10 @@ static void capture_origin(sqt_oracle *o, ring_buf *b)
 	const int S = o->p.nCSpatial, N = o->N;
 	const size_t row = 2 * NAX * (size_t)S;
 	if (o->p.flag_t) memcpy(b->org_pos, o->cur_xyz, sizeof(double) * 3 * (size_t)N);
+	if (o->p.flag_t && o->p.flag_V) memcpy(b->org_vel, o->cur_vel, sizeof(double) * 3 * (size_t)N);
 	if (o->p.flag_f) {
 		memcpy(b->org_rho, o->rho, sizeof(double) * row);
+		if (o->p.flag_V) memcpy(b->org_kvel, o->kvel, sizeof(double) * row);
 		if (o->p.flag_F) {
 			memcpy(b->org_self, o->self, sizeof(double) * N * row);
 			memcpy(b->org_dist, o->dist, sizeof(double) * N * row);
@@ -198,22 +220,33 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 	const int S = o->p.nCSpatial, T = o->p.nCTime, N = o->N;
 	const int row = 2 * NAX * S;
 	/* InitTwoTimeCorr :1315-1367 (rrMSDCM is NOT zeroed: cumulative across buffer reuse) */
-	if (o->p.flag_t) { b->msd[lag] = 0.; b->mqd[lag] = 0.; }
+	if (o->p.flag_t) { b->msd[lag] = 0.; b->mqd[lag] = 0.; if (o->p.flag_V) { b->cvv[lag] = 0.; b->cvcm[lag] = 0.; } }
 	if (o->p.flag_f) {
 		for (int nr = 0; nr < S; nr++) b->hist[nr * T + lag] = 0;
 		for (int k = 0; k < S; k++) {
 			b->F[k * T + lag] = 0.;
+			if (o->p.flag_V) { b->Cvrho[k * T + lag] = 0.; b->Crhov[k * T + lag] = 0.; b->Cvv2[k * T + lag] = 0.; }
 			if (o->p.flag_F) { b->Fs[k * T + lag] = 0.; b->Fd[k * T + lag] = 0.; }
 		}
 	}
 	/* EvalTwoTimeEach :1368-1460 (serial semantics of the racy omp loop) */
 	if (o->p.flag_t) {
 		double six = 0, siy = 0, siz = 0, sjx = 0, sjy = 0, sjz = 0;
+		double svix = 0, sviy = 0, sviz = 0, svjx = 0, svjy = 0, svjz = 0;
 		for (int n = 0; n < N; n++) {
 			const double *ri = o->cur_xyz + 3 * (size_t)n;
 			const double *rj = b->org_pos + 3 * (size_t)n;
 			six += ri[0]; siy += ri[1]; siz += ri[2];
 			sjx += rj[0]; sjy += rj[1]; sjz += rj[2];
+			double Cvv = 0;
+			if (o->p.flag_V) { /* :1397-1415 */
+				const double *vi = o->cur_vel + 3 * (size_t)n, *vj = b->org_vel + 3 * (size_t)n;
+				svix += vi[0]; sviy += vi[1]; sviz += vi[2];
+				svjx += vj[0]; svjy += vj[1]; svjz += vj[2];
+				Cvv = vi[0] * vj[0];
+				Cvv += vi[1] * vj[1];
+				Cvv += vi[2] * vj[2];
+			}
 			double dx = ri[0] - rj[0], dy = ri[1] - rj[1], dz = ri[2] - rj[2];
 			double dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;
 			double dr2 = dx2 + dy2 + dz2;
@@ -223,11 +256,18 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 			}
 			b->msd[lag] += dr2;
 			b->mqd[lag] += dr2 * dr2;
+			if (o->p.flag_V) b->cvv[lag] += Cvv;
 		}
 		double dcm = (six - sjx) * (six - sjx);
 		dcm += (siy - sjy) * (siy - sjy);
 		dcm += (siz - sjz) * (siz - sjz);
 		b->msdcm[lag] += dcm / (N * N); /* int product, as in the reference :1450 */
+		if (o->p.flag_V) { /* :1452-1457 */
+			double c = svix * svjx;
+			c += sviy * svjy;
+			c += sviz * svjz;
+			b->cvcm[lag] += c / (N * N);
+		}
 	}
 	/* EvalTwoTimeKSpace :1477-1591, w = 1 */
 	if (o->p.flag_f) {
@@ -245,6 +285,11 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 					}
 				}
 				b->F[nk * T + lag] += w * (o->rho[mR] * b->org_rho[mR] + o->rho[mI] * b->org_rho[mI]);
+				if (o->p.flag_V) { /* :1542-1555 */
+					b->Cvv2[nk * T + lag] += w * (o->kvel[mR] * b->org_kvel[mR] + o->kvel[mI] * b->org_kvel[mI]);
+					b->Crhov[nk * T + lag] += w * (o->kvel[mR] * b->org_rho[mR] + o->kvel[mI] * b->org_rho[mI]);
+					b->Cvrho[nk * T + lag] += w * (o->rho[mR] * b->org_kvel[mR] + o->rho[mI] * b->org_kvel[mI]);
+				}
 			}
 		}
 	}
@@ -258,8 +303,8 @@ static void print_process(sqt_oracle *o)
 	double inverseNptls = 1. / N;
 	double inverseNptlsSq = 1. / (N * N);
 	double average_number = 1. / (3.0 * o->countCorrAv);
-	for (int i = 0; i < 7; i++) { memcpy(o->out2d[i], o->sum2d[i], sizeof(double) * S * T); memcpy(o->rawp2d[i], o->sum2d[i], sizeof(double) * S * T); }
-	for (int i = 0; i < 3; i++) { memcpy(o->out1d[i], o->sum1d[i], sizeof(double) * T); memcpy(o->rawp1d[i], o->sum1d[i], sizeof(double) * T); }
+	for (int i = 0; i < N2D; i++) { memcpy(o->out2d[i], o->sum2d[i], sizeof(double) * S * T); memcpy(o->rawp2d[i], o->sum2d[i], sizeof(double) * S * T); }
+	for (int i = 0; i < N1D; i++) { memcpy(o->out1d[i], o->sum1d[i], sizeof(double) * T); memcpy(o->rawp1d[i], o->sum1d[i], sizeof(double) * T); }
 	if (o->p.flag_f) {
 		for (int nr = 0; nr < S; nr++)
 			for (int nt = 0; nt < T; nt++) {
@@ -270,24 +315,32 @@ static void print_process(sqt_oracle *o)
 					o->out2d[2 * q][e] = average;
 					o->out2d[2 * q + 1][e] = sqrt((averageSq - average * average));
 				}
+				if (o->p.flag_V) { /* :609-613 */
+					o->out2d[7][e] *= inverseNptls * average_number;
+					o->out2d[8][e] *= inverseNptls * average_number;
+					o->out2d[9][e] *= inverseNptls * average_number;
+				}
 			}
 		for (int nt = 1; nt < T; nt++)
 			for (int nr = 0; nr < S; nr++) o->out2d[6][nr * T + nt] *= o->factorDr[nr];
 	}
 	double scale_factor = 1. / (N * o->countCorrAv);
 	double factor_msdcm = 1. / (o->countCorrAv);
+	double factor_Cvv = 1. / (N * o->countCorrAv * 3.);   /* :640-642 */
+	double factor_Cvcmvcm = 1. / (o->countCorrAv * 3.);
 	if (o->p.flag_t)
 		for (int nt = 0; nt < T; nt++) {
 			o->out1d[0][nt] *= scale_factor;
 			o->out1d[2][nt] *= factor_msdcm;
 			o->out1d[1][nt] *= scale_factor;
+			if (o->p.flag_V) { o->out1d[3][nt] *= factor_Cvv; o->out1d[4][nt] *= factor_Cvcmvcm; }
 		}
 	o->n_print++;
 	o->printed_count = o->countCorrAv;
 	/* ZeroAvSpacetimeCorr :477-540 */
 	o->countCorrAv = 0;
-	for (int i = 0; i < 7; i++) memset(o->sum2d[i], 0, sizeof(double) * S * T);
-	for (int i = 0; i < 3; i++) memset(o->sum1d[i], 0, sizeof(double) * T);
+	for (int i = 0; i < N2D; i++) memset(o->sum2d[i], 0, sizeof(double) * S * T);
+	for (int i = 0; i < N1D; i++) memset(o->sum1d[i], 0, sizeof(double) * T);
 }
 
 /* AccumSpacetimeCorr, lmp2sqt.c:368-444. */
@@ -310,6 +363,11 @@ static int accumulate(sqt_oracle *o)
 						o->sum2d[4][e] += b->Fd[e];
 						o->sum2d[5][e] += b->Fd[e] * b->Fd[e];
 					}
+					if (o->p.flag_V) { /* :394-398 */
+						o->sum2d[7][e] += b->Cvrho[e];
+						o->sum2d[8][e] += b->Crhov[e];
+						o->sum2d[9][e] += b->Cvv2[e];
+					}
 				}
 			for (int nt = 0; nt < T; nt++)
 				for (int nr = 0; nr < S; nr++) o->sum2d[6][nr * T + nt] += b->hist[nr * T + nt];
@@ -319,6 +377,7 @@ static int accumulate(sqt_oracle *o)
 				o->sum1d[0][nt] += b->msd[nt];
 				o->sum1d[2][nt] += b->msdcm[nt];
 				o->sum1d[1][nt] += b->mqd[nt];
+				if (o->p.flag_V) { o->sum1d[3][nt] += b->cvv[nt]; o->sum1d[4][nt] += b->cvcm[nt]; } /* :423-426 */
 			}
 		b->count = 0;
 		++o->countCorrAv;
@@ -330,6 +389,12 @@ static int accumulate(sqt_oracle *o)
 /* EvalSpacetimeCorr, lmp2sqt.c:1599-1650. */
 int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, double xhi)
 {
+	return sqt_oracle_push_frame_v(o, xyz, NULL, n, xlo, xhi);
+}
+
+int sqt_oracle_push_frame_v(sqt_oracle *o, const double *xyz, const double *vel, int n, double xlo, double xhi)
+{
+	if (o->p.flag_V && !vel) return -2;
 	if (o->nSkip < o->p.nCSkip) { o->nSkip++; return 0; }
 	o->L = xhi - xlo;
 	o->vol = o->L * o->L * o->L;
@@ -337,6 +402,7 @@ int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, d
 	if (n != o->N) return -1;
 	o->kVal = 2. * M_PI / o->L;
 	o->cur_xyz = xyz;
+	o->cur_vel = vel;
 	if (o->p.flag_f) one_time_kspace(o);
 	for (int nb = 0; nb < o->p.nCBuffer; nb++) {
 		ring_buf *b = &o->buf[nb];
@@ -347,6 +413,7 @@ int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, d
 	int printed = accumulate(o);
 	o->nSkip = 0;
 	o->cur_xyz = NULL;
+	o->cur_vel = NULL;
 	return printed;
 }
 

@@ -9,7 +9,8 @@
  * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this restatement
  * against the unmodified reference (oracle/_ref/liblmp2sqt_ref.so built from
  * /root/reference by oracle/Makefile) and against the committed golden files in
- * tests/golden/ that the reference binary itself produced.
+ * tests/golden/ that the reference binary itself produced.  The -V (velocity) correlators are restated
+ * and pinned the same way ahead of the product code (tests/golden/velocity).
  */
 #ifndef SQT_ORACLE_H
 #define SQT_ORACLE_H
@@ -25,6 +26,7 @@ typedef struct {
 	double kVal, deltaT, mass, rVal;
 	int limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip;
 	int flag_f, flag_F, flag_t;
+	int flag_V; /* -V (flag_velocity, lmp2sqt.c:172): current correlators C2_v_v / C2_rho_v / C2_v_rho, Cvv, Cvcmvcm */
 } sqt_oracle_params;
 
 sqt_oracle *sqt_oracle_create(const sqt_oracle_params *p);
@@ -39,6 +41,8 @@ void sqt_oracle_begin_file(sqt_oracle *o);
  * results were stored in the "printed" arrays and the averages were zeroed;
  * 0 otherwise; <0 on error. */
 int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, double xhi);
+/* The same with velocities, AoS [n][3] (required when flag_V is set). */
+int sqt_oracle_push_frame_v(sqt_oracle *o, const double *xyz, const double *vel, int n, double xlo, double xhi);
 
 /* End-of-run print (lmp2sqt.c:327-333): only if nothing was printed before,
  * limitCorrAv = countCorrAv, then PrintProcess.  Returns 1 if it printed now. */
@@ -58,10 +62,11 @@ int sqt_oracle_buffer_count(const sqt_oracle *o, int nb);
 /* Arrays.  "raw" = running sums before normalisation; "printed" = what
  * prePrintProcess (lmp2sqt.c:576-675) left in the arrays at the last print.
  * 2-D arrays are [nCSpatial][nCTime] row-major (the reference's avF_qq2[nk][nt]).
- * which: 0 avF, 1 StdDevF, 2 avF_s, 3 StdDevF_s, 4 avF_d, 5 StdDevF_d, 6 avDrTable */
+ * which: 0 avF, 1 StdDevF, 2 avF_s, 3 StdDevF_s, 4 avF_d, 5 StdDevF_d, 6 avDrTable,
+ *        7 avC2_v_rho, 8 avC2_rho_v, 9 avC2_v_v (flag_V) */
 const double *sqt_oracle_raw2d(const sqt_oracle *o, int which);
 const double *sqt_oracle_printed2d(const sqt_oracle *o, int which);
-/* which: 0 rrMSDAv, 1 rrMQDAv, 2 rrMSDCMAv  (length nCTime) */
+/* which: 0 rrMSDAv, 1 rrMQDAv, 2 rrMSDCMAv, 3 rrCvvAv, 4 rrCvcmvcmAv (flag_V)  (length nCTime) */
 const double *sqt_oracle_raw1d(const sqt_oracle *o, int which);
 const double *sqt_oracle_printed1d(const sqt_oracle *o, int which);
 /* the raw sums as they stood when the last print normalised them (input of prePrintProcess) */

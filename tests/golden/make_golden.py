@@ -48,6 +48,11 @@ CASES = {
     "g6_nCS70": dict(traj=[dict(n_cells=3, n_atoms=100, n_frames=36, seed=7, box_jitter=0.005)], S=70, T=8, B=8, skip=None, limit=14825, flags="Ft"),
     "g7_nCS128": dict(traj=[dict(n_cells=3, n_frames=30, seed=8)], S=128, T=6, B=3, skip=None, limit=14825, flags="Ft"),
 }
+# SURVEY.md section 8f.4 (next row, oracle first): -V, dumps with vx vy vz.  Kept apart from CASES: the product's host
+# code and engine do not implement -V yet, only oracle/sqt_oracle.c does; tests/test_oracle.py pins it on this case.
+CASES_V = {
+    "v1_velocity": dict(traj=[dict(n_cells=2, n_frames=40, seed=9, box_jitter=0.005)], S=5, T=8, B=4, skip=None, limit=14825, flags="FtV"),
+}
 
 
 def main():
@@ -55,10 +60,11 @@ def main():
     assert pyoracle.have_reference(), "needs /root/reference"
     here = os.path.dirname(os.path.abspath(__file__))
     only = sys.argv[1:]                                   # optional: regenerate just the named cases
-    for name, c in CASES.items():
+    for name, c in list(CASES.items()) + list(CASES_V.items()):
         if only and name not in only:
             continue
-        out = os.path.join(here, name)
+        vel = "V" in c["flags"]
+        out = os.path.join(here, "velocity", name) if vel else os.path.join(here, name)
         shutil.rmtree(out, ignore_errors=True)
         os.makedirs(out)
         trajs = [synth.make_trajectory(**kw) for kw in c["traj"]]
@@ -66,12 +72,12 @@ def main():
             dumps = []
             for i, t in enumerate(trajs):
                 dn = "dump%d.lammpstrj" % i
-                synth.write_text_dump(t, os.path.join(td, dn))
+                synth.write_text_dump(t, os.path.join(td, dn), velocities=vel)
                 dumps.append(dn)
             synth.write_deck(os.path.join(td, "in.lmp2sqt"), limitCorrAv=c["limit"], nCBuffer=c["B"],
                              nCSpatial=c["S"], nCTime=c["T"], nCSkip=c["skip"])
             shutil.copy(os.path.join(td, "in.lmp2sqt"), os.path.join(out, "in.lmp2sqt"))
-            cli_flags = {"Ft": ("-F", "-t"), "ft": ("-f", "-t"), "F": ("-F",), "t": ("-t",)}[c["flags"]]
+            cli_flags = {"Ft": ("-F", "-t"), "ft": ("-f", "-t"), "F": ("-F",), "t": ("-t",), "FtV": ("-F", "-t", "-V")}[c["flags"]]
             r = pyoracle.run_reference_cli(td, "in.lmp2sqt", dumps, flags=cli_flags, threads=1)
             assert r.returncode == 0, r.stderr
             with open(os.path.join(out, "stdout.txt"), "w") as f:
@@ -80,7 +86,8 @@ def main():
             for fn in ("output.binary", "output.txt", "output.log"):
                 if os.path.exists(os.path.join(td, fn)):
                     shutil.copy(os.path.join(td, fn), os.path.join(out, fn))
-            for pat, dst in (("SSF000.info.*", "SSF000.info"), ("Dt000.info.*", "Dt000.info")):
+            vel_files = (("C2_v_v000.info.*", "C2_v_v000.info"), ("C2_v_rho000.info.*", "C2_v_rho000.info"), ("C2_rho_v000.info.*", "C2_rho_v000.info")) if vel else ()
+            for pat, dst in (("SSF000.info.*", "SSF000.info"), ("Dt000.info.*", "Dt000.info")) + vel_files:
                 g = glob.glob(os.path.join(td, pat))
                 if g:
                     shutil.copy(g[0], os.path.join(out, dst))

@@ -94,3 +94,58 @@ def test_known_answer_identities_on_the_oracle():
     m = np.arange(1, 5)[:, None]; tau = np.arange(5)[None, :]
     np.testing.assert_allclose(pr["avF_s"], (np.cos(m * k0 * 0.1 * tau) + 2) / 3, rtol=1e-10)
     np.testing.assert_allclose(pr["rrMSDAv"], 0.01 * tau[0] ** 2, rtol=1e-9)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("flags", ["FtV", "ftV"])
+def test_port_velocity_correlators_bit_identical_to_live_reference(flags):
+    """SURVEY.md section 8f.4, oracle first: the restatement of the -V path (current density k v e^{ikr}, its
+    correlators C2_v_v / C2_rho_v / C2_v_rho, the velocity autocorrelation Cvv and Cvcmvcm; lmp2sqt.c:1203-1208,
+    1397-1457, 1542-1555, 609-613, 640-652) against the unmodified reference run with flag_velocity on the same frames."""
+    t1 = synth.make_trajectory(n_cells=2, n_frames=43, box_jitter=0.01, seed=303)
+    t2 = synth.make_trajectory(n_cells=2, n_frames=29, box_jitter=0.01, seed=404)
+    S, T, B = 6, 8, 4
+    ref = pyoracle.run_reference([t1, t2], S, T, B, limit=1000, flags=flags)
+    extra = sum((t.n_frames - T) // (T // B) for t in (t1, t2))
+    pr, raw, log = pyoracle.run_port(None, S, T, B, limitCorrAv=1000 - extra, files=[t1, t2], flags=flags)
+    assert ref["raw"]["countCorrAv"] == raw["countCorrAv"] and ref["log"] == [l[0] for l in log]
+    names = N2 + N1 + pyoracle.NAMES2D_V + pyoracle.NAMES1D_V
+    for k in names:
+        assert np.array_equal(ref["raw"][k], raw[k]), k
+        assert np.array_equal(ref["printed"][k], pr[k], equal_nan=True), k
+    assert np.abs(raw["avC2_v_v"]).max() > 0 and np.abs(raw["rrCvvAv"]).max() > 0   # the -V path really ran
+    # without -V nothing of it leaks into the standard arrays
+    pr0, raw0, _ = pyoracle.run_port(None, S, T, B, limitCorrAv=1000 - extra, files=[t1, t2], flags=flags.replace("V", ""))
+    for k in N2 + N1:
+        assert np.array_equal(raw0[k], raw[k]), k
+
+
+def test_port_velocity_correlators_reproduce_committed_reference_fixture():
+    """The same -V restatement against a COMMITTED fixture (tests/golden/velocity/v1_velocity: written by the unmodified
+    reference CLI with -F -t -V on a dump that carries vx vy vz, plus the raw fp64 sums read from its globals), so that
+    the check also runs where /root/reference does not exist."""
+    import gzip
+    import json
+    from golden_utils import GOLDEN, read_dump_text
+    d = os.path.join(GOLDEN, "velocity", "v1_velocity")
+    c = json.load(open(os.path.join(d, "case.json")))
+    a = dict(np.load(os.path.join(d, "arrays.npz")))
+    with gzip.open(os.path.join(d, "dump0.lammpstrj.gz"), "rt") as f:
+        traj = read_dump_text(f.read())
+    assert traj.velocities is not None and traj.velocities.shape == traj.positions.shape
+    S, T, B = c["S"], c["T"], c["B"]
+    extra = (traj.n_frames - T) // (T // B)
+    printed, raw, log = pyoracle.run_port(None, S, T, B, limitCorrAv=10**9 - extra, files=[traj], flags=c["flags"], finish=False)
+    assert raw["countCorrAv"] == int(a["raw_countCorrAv"]) and [l[0] for l in log] == list(a["count_log"])
+    for k in N2 + N1 + pyoracle.NAMES2D_V + pyoracle.NAMES1D_V:
+        assert np.array_equal(raw[k], a["raw_" + k]), k
+    # what the reference printed: the Dt file's Cvv / Cvcmvcm columns (%8.4f / %8.4g) and the C2 tables (%8.4e)
+    printed, _, _ = pyoracle.run_port(None, S, T, B, limitCorrAv=c["limit"], files=[traj], flags=c["flags"])
+    rows = [ln.split() for ln in open(os.path.join(d, "Dt000.info")).read().strip().split("\n")[1:]]
+    for nt, r in enumerate(rows):
+        assert r[8] == ("%8.4f" % printed["rrCvvAv"][nt]).strip() and r[9] == ("%8.4g" % printed["rrCvcmvcmAv"][nt]).strip()
+    for fn, key in (("C2_v_v000.info", "avC2_v_v"), ("C2_rho_v000.info", "avC2_rho_v"), ("C2_v_rho000.info", "avC2_v_rho")):
+        tab = [ln.split() for ln in open(os.path.join(d, fn)).read().strip().split("\n")]
+        assert len(tab) == T
+        for nt, r in enumerate(tab):
+            assert r[1:] == [("%8.4e" % printed[key][nk, nt]).strip() for nk in range(S)], (fn, nt)
