@@ -124,6 +124,11 @@ int sqt_dump_read_atoms(FILE *fp, const sqt_frame_header *hd, double *x, double 
 		x[i] = next_real(&c, &ok);
 		y[i] = next_real(&c, &ok);
 		z[i] = next_real(&c, &ok);
+		/* the wider styles' columns (vx vy vz / mux muy muz) are not used, but the reference parses them: a line that lacks
+		 * them is a short line (snapshot.c:268-330).  Three more tokens in every wider style: the 11-column header also
+		 * matches the reference's 8-column "mux muy muz" prefix test, which comes first (snapshot.c:262) */
+		for (int k = hd->style ? 3 : 0; k > 0; k--)
+			if (!skip_token(&c)) ok = 0;
 	}
 	return 1;
 }

@@ -270,7 +270,7 @@ static inline const char *fast_real(const char *p, const char *lim, double *out)
 	return p;
 }
 
-static inline const char *fast_line(const char *p, double *x, double *y, double *z)
+static inline const char *fast_line(const char *p, const int extra, double *x, double *y, double *z)
 {
 	const char *lim = p + FAST_SCAN;
 #define SKIP_SPACES while (*p == ' ' && p < lim) p++
@@ -291,10 +291,24 @@ static inline const char *fast_line(const char *p, double *x, double *y, double 
 	if (!(p = fast_real(p, lim, z))) return NULL;
 #undef SKIP_SPACES
 #undef SKIP_DIGITS
-	if (*p == '\n') return p + 1;
-	if (p >= lim) return NULL;
-	const char *nl = (const char *)memchr(p, '\n', 128); /* trailing columns (velocities, ...) or \r */
-	return nl ? nl + 1 : NULL;
+	if (extra == 0) {
+		if (*p == '\n') return p + 1;
+		if (p >= lim) return NULL;
+		const char *nl = (const char *)memchr(p, '\n', 128); /* trailing blanks or \r */
+		return nl ? nl + 1 : NULL;
+	}
+	/* wider styles (vx vy vz / mux muy muz): the columns are not used, but the reference parses them -- a line that lacks
+	 * them is a short line (snapshot.c:268-330), which only the general path judges */
+	int tokens = 0;
+	const char *end = lim + 128;
+	for (;;) {
+		while (*p == ' ' && p < end) p++;
+		if (*p == '\n' || p >= end) break;
+		tokens++;
+		while (*p != ' ' && *p != '\n' && p < end) p++;
+	}
+	if (*p != '\n' || tokens < extra) return NULL;
+	return p + 1;
 }
 
 sqt_reader *sqt_reader_open(const char *path, int n_threads)
@@ -524,6 +538,7 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 	if (r->blk_cursor < r->n_blk && r->blk[r->blk_cursor].atoms_pos == r->pos && r->blk[r->blk_cursor].n_atoms == n) bi = &r->blk[r->blk_cursor];
 	if (bi) endp = bi->end_pos;
 	else if (!index_lines(r, n, step, starts, T, &endp)) { r->pos = r->size; return 0; }
+	const int extra = hd->style ? 3 : 0; /* also for the 11-column style: the reference's 8-column prefix test matches it first (snapshot.c:262) */
 	int bad = 0;
 #ifdef _OPENMP
 #pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : bad) if (T > 1)
@@ -541,7 +556,7 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 		} else pos = starts[t];
 		for (int i = i0; i < i1; i++) {
 			if (r->size - pos > FAST_MARGIN) { /* far enough from the end of the mapping for the unchecked scan */
-				const char *nx = fast_line(r->base + pos, &x[i], &y[i], &z[i]);
+				const char *nx = fast_line(r->base + pos, extra, &x[i], &y[i], &z[i]);
 				if (nx) { pos = (size_t)(nx - r->base); continue; }
 			}
 			const char *p, *e;
@@ -552,6 +567,8 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 			x[i] = tok_real(&c, e, &ok);
 			y[i] = tok_real(&c, e, &ok);
 			z[i] = tok_real(&c, e, &ok);
+			for (int k = extra; k > 0; k--)
+				if (!tok_skip(&c, e)) ok = 0;              /* unused columns of the wider styles must be there too */
 			if (!ok && i != n - 1) bad |= 1; /* a short line fails the frame unless it is the last (snapshot.c:352-356) */
 		}
 	}
