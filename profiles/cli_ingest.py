@@ -5,8 +5,8 @@ usage: python profiles/cli_ingest.py [n_frames=40]"""
 import json, os, subprocess, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import pyoracle
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from outbin import parse_output_binary
 from lmp2sqt_b200 import _lib, synth
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 40
@@ -26,6 +26,6 @@ with tempfile.TemporaryDirectory() as td:
         w = time.time() - t0
         assert r.returncode == 0, r.stderr[-500:]
         res[kind] = {"file_MB": os.path.getsize(dump) / 1e6, "wall_s": w, "atoms_per_s_two_passes": 2 * traj.n_atoms * frames / w}
-        out[kind] = pyoracle.parse_output_binary(os.path.join(d, "output.binary"), S, T)
+        out[kind] = parse_output_binary(os.path.join(d, "output.binary"), S, T)
     res["outputs_equal"] = all(np.allclose(out["text"][k], out["raw"][k], rtol=1e-11, atol=1e-12) for k in ("full-density", "self-density", "self-vanHove"))
     print(json.dumps(res))
