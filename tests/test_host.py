@@ -432,3 +432,19 @@ def test_mmap_reader_indexed_parse_pass_equals_plain_parse(tmp_path, threads, tr
     cut = tmp_path / "cut.lammpstrj"
     cut.write_bytes(p.read_bytes()[:-4000])
     assert len(_read_all_frames_mmap_two_pass(str(cut), threads)) == 2
+
+
+def test_integration_snippet_compiles_and_links(tmp_path):
+    """INTEGRATION.md section 2 is real code: the documented call sequence compiles against include/*.h and links against
+    the two shared libraries (not run here: it needs a GPU)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "lmp2sqt_b200")
+    exe = tmp_path / "snippet"
+    env = {k: v for k, v in os.environ.items() if k != "CC"}
+    r = subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "data", "integration_snippet.c"), "-L", pkg, "-lsqt_b200", "-lsqt_host", "-lm",
+                        "-Wl,-rpath," + pkg, "-o", str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2                                 # usage path: the binary loads both libraries and starts
