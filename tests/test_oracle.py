@@ -149,3 +149,36 @@ def test_port_velocity_correlators_reproduce_committed_reference_fixture():
         assert len(tab) == T
         for nt, r in enumerate(tab):
             assert r[1:] == [("%8.4e" % printed[key][nk, nt]).strip() for nk in range(S)], (fn, nt)
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(16))
+def test_port_bit_identical_to_live_reference_random_sweep(seed):
+    """Random decks (nCSpatial, ring shape incl. nCBuffer > nCTime, nCSkip), flag sets (incl. -V) and file sets (short files
+    are skipped like main() does): raw sums, ring bookkeeping per frame and the normalised arrays, bit for bit."""
+    rng = np.random.default_rng(7000 + seed)
+    S, T = int(rng.integers(1, 9)), int(rng.integers(2, 10))
+    B = int(rng.integers(1, T + 3))
+    skip = int(rng.integers(0, 3))
+    flags = str(rng.choice(["Ft", "ft", "FtV", "ftV"]))
+    Bc = max(1, min(B, T))
+    trajs = []
+    for i in range(int(rng.integers(1, 4))):
+        frames = int(rng.choice([T + 1 + T // Bc, 2 * T + 3, 3 * T + 1, 40]))
+        trajs.append(synth.make_trajectory(n_cells=int(rng.integers(1, 3)) if i == 0 else 1, n_frames=frames, seed=int(rng.integers(0, 10**6)),
+                                           box_jitter=float(rng.choice([0.0, 0.01]))))
+    n0 = trajs[0].n_atoms
+    trajs = [t for t in trajs if t.n_atoms == n0]                      # one atom count per run
+    # only files main() accepts (lmp2sqt.c:221-236): run_port applies that rule, the in-process reference driver does not
+    trajs = [t for t in trajs if t.n_frames >= 5 and int((t.n_frames - T) / (T // Bc)) >= 1]
+    if not trajs:
+        pytest.skip("no acceptable file in this draw")
+    extra = sum((t.n_frames - T) // (T // Bc) for t in trajs if t.n_frames >= 5 and (t.n_frames - T) // (T // Bc) >= 1)
+    ref = pyoracle.run_reference(trajs, S, T, B, nCSkip=skip, limit=1000, flags=flags)
+    pr, raw, log = pyoracle.run_port(None, S, T, B, nCSkip=skip, limitCorrAv=1000 - extra, files=trajs, flags=flags)
+    assert ref["raw"]["countCorrAv"] == raw["countCorrAv"] and ref["log"] == [l[0] for l in log]
+    names = N2 + N1 + (pyoracle.NAMES2D_V + pyoracle.NAMES1D_V if "V" in flags else [])
+    for k in names:
+        assert np.array_equal(ref["raw"][k], raw[k]), k
+        if raw["countCorrAv"] > 0:
+            assert np.array_equal(ref["printed"][k], pr[k], equal_nan=True), k
