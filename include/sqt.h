@@ -49,10 +49,18 @@ typedef struct sqt_handle sqt_handle;
 typedef struct {
 	double kVal, deltaT, mass, rVal;
 	int limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip;
-	int flag_f, flag_F, flag_t;
-	int device;          /* CUDA device ordinal this handle owns */
-	int reserved[7];     /* must be zero */
+	int flag_f, flag_F, flag_t;   /* -f: F(q,t) and rho(k); -F: also F_s / F_d; -t: MSD, MQD, MSDCM and (with -f) the van Hove table.
+	                               * The engine only runs what the flags ask for (lmp2sqt.c:1246-1249, 1370, 1479) */
+	int device;          /* CUDA device ordinal this handle owns (sqt_create); first device of sqt_multi_create */
+	int n_gpus;          /* sqt_multi_create: GPUs device .. device + n_gpus - 1, particle-sharded in this process; 0 = 1 */
+	int flag_V;          /* -V (flag_velocity, lmp2sqt.c:172): current correlators; frames then carry vx vy vz */
+	int reserved[5];     /* must be zero */
 } sqt_params;
+
+/* Largest nCSpatial the kernels cover (the reference accepts any; a deck beyond this is refused by sqt_create).  With
+ * flag_V the limit is 256 (the current density comes from the tensor-core rho(k) kernel). */
+#define SQT_MAX_NCSPATIAL 1024
+#define SQT_MAX_NCSPATIAL_V 256
 
 /*
  * Raw running sums, exactly the arrays prePrintProcess (lmp2sqt.c:576-675) consumes, before
@@ -72,6 +80,10 @@ typedef struct {
 	double *avF_qq2, *StdDevF_qq2, *avF_s_qq2, *StdDevF_s_qq2, *avF_d_qq2, *StdDevF_d_qq2;
 	double *avDrTable;
 	double *rrMSDAv, *rrMQDAv, *rrMSDCMAv;   /* [nCTime] */
+	/* -V only (zero otherwise): avC2_v_rho, avC2_rho_v, avC2_v_v [nCSpatial][nCTime] (lmp2sqt.c:394-398), rrCvvAv,
+	 * rrCvcmvcmAv [nCTime] (:423-426) */
+	double *avC2_v_rho, *avC2_rho_v, *avC2_v_v;
+	double *rrCvvAv, *rrCvcmvcmAv;
 } sqt_results;
 
 int  sqt_results_alloc(sqt_results *r, int nCSpatial, int nCTime);
@@ -92,8 +104,8 @@ int  sqt_begin_file(sqt_handle *h);
 
 /* ---- frames ------------------------------------------------------------------------------ */
 /* Pinned host staging for the next frame, SoA: x[0..n), y[0..n), z[0..n) as doubles
- * (3*n_atoms_local contiguous).  Double buffered: the pointer stays valid until the second
- * following sqt_stage_acquire.  Blocks only if the slot's previous H2D copy is still in flight. */
+ * (3*n_atoms_local contiguous; with flag_V six arrays: x y z vx vy vz).  Double buffered: the pointer stays valid
+ * until the second following sqt_stage_acquire.  Blocks only if the slot's previous H2D copy is still in flight. */
 double *sqt_stage_acquire(sqt_handle *h, int n_atoms_local);
 
 /* EvalSpacetimeCorr (lmp2sqt.c:1599-1650) for one frame.  `soa` is either a buffer from
@@ -105,10 +117,21 @@ double *sqt_stage_acquire(sqt_handle *h, int n_atoms_local);
  * Returns SQT_OK, SQT_FLUSH, or <0. */
 int  sqt_push_frame(sqt_handle *h, const double *soa, int n_atoms_local, long long n_atoms_total,
                     double xlo, double xhi);
-/* Same, for a frame already resident in device memory (SoA, 3*n_atoms_local doubles) on
- * the handle's device -- the binary / on-device frame source path. */
+/* Same with one pointer per component (this handle's slice of a caller-owned SoA frame; vx/vy/vz may be NULL unless
+ * flag_V).  Pinned memory is copied asynchronously and must stay unmodified until two further pushes or sqt_sync. */
+int  sqt_push_frame_xyz(sqt_handle *h, const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                        const double *vz, int n_atoms_local, long long n_atoms_total, double xlo, double xhi);
+/* Same, for a frame already resident in device memory (SoA, 3*n_atoms_local doubles; 6*n with flag_V) on
+ * the handle's device -- the binary / on-device frame source path.
+ * Stream ordering: the engine copies d_soa on its own (blocking) stream.  A producer that fills d_soa on the legacy
+ * default stream is ordered automatically; a producer on any other stream (cudaStreamNonBlocking, per-thread default
+ * stream, a torch side stream) must either synchronise before the call or use the _ex variant. */
 int  sqt_push_frame_device(sqt_handle *h, const double *d_soa, int n_atoms_local,
                            long long n_atoms_total, double xlo, double xhi);
+/* producer_stream: the cudaStream_t (passed as void *) that wrote d_soa.  The engine's copy waits for the work enqueued on
+ * it so far, and work enqueued on it after the call waits for the engine's copy, so the producer may refill d_soa. */
+int  sqt_push_frame_device_ex(sqt_handle *h, const double *d_soa, int n_atoms_local,
+                              long long n_atoms_total, double xlo, double xhi, void *producer_stream);
 
 /* ---- results ----------------------------------------------------------------------------- */
 /* After SQT_FLUSH: the sums latched at the flush (the averages were zeroed on the device
@@ -124,8 +147,12 @@ int  sqt_sync(sqt_handle *h);
 int  sqt_count_corr_av(const sqt_handle *h);
 int  sqt_buffer_count(const sqt_handle *h, int nb);       /* TBuf.count, lmp2sqt.h:69 */
 int  sqt_number_call_print(const sqt_handle *h);
-/* rho(k) of the last processed frame, [3][nCSpatial][2] (marker layout lmp2sqt.c:1173-1174). */
+/* rho(k) of the last processed frame, [3][nCSpatial][2] (marker layout lmp2sqt.c:1173-1174), reduced over all shards.
+ * Waits only for that frame's rho(k) kernel, its allreduce and the F(q,t) update -- not for the frame's self-term kernel,
+ * which keeps running while the caller prepares the next frame. */
 int  sqt_get_rho(sqt_handle *h, double *out);
+/* With flag_V: the current density kvel_q1 of the last processed frame, same layout (lmp2sqt.c:1203-1208). */
+int  sqt_get_kvel(sqt_handle *h, double *out);
 long long sqt_kernel_launches(const sqt_handle *h);       /* launches of OUR kernels so far */
 /* CUDA-event timing of a frame's dominant kernels on their own stream: the self-term kernel of the family in
  * use (self_ring_mma_kernel / self_ring_vec_kernel / self_ring_kernel) plus the rho(k) kernel, one event pair around
@@ -147,6 +174,28 @@ const char *sqt_kernel_config(const sqt_handle *h);
 #define SQT_COMM_ID_BYTES 128
 int  sqt_comm_unique_id(void *id_out);
 int  sqt_comm_init(sqt_handle *h, const void *id, int rank, int nranks);
+
+/* ---- multi-GPU inside one process: one reader, frame fan-out to G GPUs ------------------
+ * The reference's frame loop (lmp2sqt.c:292-320) stays single threaded in the caller: it fills ONE pinned SoA frame
+ * (sqt_multi_stage_acquire) and pushes it; the library owns G engine handles on devices p->device .. p->device +
+ * p->n_gpus - 1, one worker thread and one NCCL rank per GPU, splits the frame into G contiguous particle chunks
+ * (dump order) and issues one asynchronous H2D copy per component and GPU.  Results are identical on every rank;
+ * they are fetched from rank 0.  Same call sequence and return codes as the single-handle API. */
+typedef struct sqt_multi sqt_multi;
+int  sqt_multi_create(const sqt_params *p, sqt_multi **out);
+void sqt_multi_destroy(sqt_multi *m);
+const char *sqt_multi_last_error(const sqt_multi *m);
+int  sqt_multi_n_gpus(const sqt_multi *m);
+sqt_handle *sqt_multi_handle(sqt_multi *m, int rank);      /* introspection only */
+int  sqt_multi_set_limit(sqt_multi *m, int limitCorrAv);
+int  sqt_multi_begin_file(sqt_multi *m);
+/* pinned (portable) SoA for a whole frame: x[n] y[n] z[n] (+ vx[n] vy[n] vz[n] with flag_V); double buffered */
+double *sqt_multi_stage_acquire(sqt_multi *m, int n_atoms);
+int  sqt_multi_push_frame(sqt_multi *m, const double *soa, int n_atoms, double xlo, double xhi);
+int  sqt_multi_fetch_results(sqt_multi *m, sqt_results *out);
+int  sqt_multi_finish(sqt_multi *m, sqt_results *out);
+int  sqt_multi_sync(sqt_multi *m);
+long long sqt_multi_kernel_launches(const sqt_multi *m);
 
 /* ---- on-device synthetic frame source (bench workloads) ------------ */
 typedef struct sqt_synth sqt_synth;

@@ -74,17 +74,25 @@ void sqt_reader_close(sqt_reader *r);
 void sqt_reader_rewind(sqt_reader *r);
 int sqt_reader_next_header(sqt_reader *r, sqt_frame_header *hd);
 int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z);
+/* -V: the same with the velocity columns of the `id type xu yu zu vx vy vz` style (snapshot.c:285-300).  Any other style
+ * fails the frame: the reference would correlate uninitialised memory there (make_atom / make_atom_dipole never set vx). */
+int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz);
 int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd);
 
 /* factorDr[nr], lmp2sqt.c:1987-2009, from what the engine recorded at the first processed frame. */
 void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr);
 /* prePrintProcess: normalises r's arrays IN PLACE (like the reference does with its globals). */
 void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t);
+void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V);
 /* PrintProcess: normalise, then write SSF%03d.info.<date>, Dt%03d.info.<date>, output.txt,
  * output.binary, output.log into `dir` (NULL = cwd).  `date` is the yymmdd suffix (NULL = today,
  * lmp2sqt.c:127-132).  Returns 0 or -1. */
 int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t,
                            const char *date);
+/* The same with -V: also normalises the current correlators and writes C2_v_v / C2_v_rho / C2_rho_v%03d.info.<date> and the
+ * Cvv, Cvcmvcm columns of the Dt file (lmp2sqt.c:933-993, 1033-1076). */
+int sqt_host_print_process_v(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V,
+                             const char *date);
 
 /* ---- post-processing of the correlators (reference: analysis_binary.c) ---------------------
  * Tables are [k][t] (k-major) like the reference's corrSum.  Sequence: load (or from_results) -> time | fourier -> print. */

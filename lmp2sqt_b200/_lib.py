@@ -22,7 +22,7 @@ class SqtParams(C.Structure):
     _fields_ = [("kVal", C.c_double), ("deltaT", C.c_double), ("mass", C.c_double), ("rVal", C.c_double),
                 ("limitCorrAv", C.c_int), ("nCBuffer", C.c_int), ("nCSpatial", C.c_int), ("nCTime", C.c_int),
                 ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int),
-                ("device", C.c_int), ("reserved", C.c_int * 7)]
+                ("device", C.c_int), ("n_gpus", C.c_int), ("flag_V", C.c_int), ("reserved", C.c_int * 5)]
 
 
 _PD = C.POINTER(C.c_double)
@@ -34,7 +34,8 @@ class SqtResults(C.Structure):
                 ("first_limitCorrAv", C.c_int), ("number_call_print", C.c_int),
                 ("avF_qq2", _PD), ("StdDevF_qq2", _PD), ("avF_s_qq2", _PD), ("StdDevF_s_qq2", _PD),
                 ("avF_d_qq2", _PD), ("StdDevF_d_qq2", _PD), ("avDrTable", _PD),
-                ("rrMSDAv", _PD), ("rrMQDAv", _PD), ("rrMSDCMAv", _PD)]
+                ("rrMSDAv", _PD), ("rrMQDAv", _PD), ("rrMSDCMAv", _PD),
+                ("avC2_v_rho", _PD), ("avC2_rho_v", _PD), ("avC2_v_v", _PD), ("rrCvvAv", _PD), ("rrCvcmvcmAv", _PD)]
 
 
 class SqtDeck(C.Structure):
@@ -69,7 +70,9 @@ ENGINE_API = [
     ("sqt_begin_file", C.c_int, [C.c_void_p]),
     ("sqt_stage_acquire", C.c_void_p, [C.c_void_p, C.c_int]),
     ("sqt_push_frame", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double]),
+    ("sqt_push_frame_xyz", C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int, C.c_longlong, C.c_double, C.c_double]),
     ("sqt_push_frame_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double]),
+    ("sqt_push_frame_device_ex", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_void_p]),
     ("sqt_fetch_results", C.c_int, [C.c_void_p, C.POINTER(SqtResults)]),
     ("sqt_finish", C.c_int, [C.c_void_p, C.POINTER(SqtResults)]),
     ("sqt_sync", C.c_int, [C.c_void_p]),
@@ -77,6 +80,7 @@ ENGINE_API = [
     ("sqt_buffer_count", C.c_int, [C.c_void_p, C.c_int]),
     ("sqt_number_call_print", C.c_int, [C.c_void_p]),
     ("sqt_get_rho", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("sqt_get_kvel", C.c_int, [C.c_void_p, C.c_void_p]),
     ("sqt_kernel_launches", C.c_longlong, [C.c_void_p]),
     ("sqt_profile_enable", C.c_int, [C.c_void_p, C.c_int]),
     ("sqt_profile_read", C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
@@ -85,6 +89,19 @@ ENGINE_API = [
     ("sqt_kernel_config", C.c_char_p, [C.c_void_p]),
     ("sqt_comm_unique_id", C.c_int, [C.c_void_p]),
     ("sqt_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    ("sqt_multi_create", C.c_int, [C.POINTER(SqtParams), C.POINTER(C.c_void_p)]),
+    ("sqt_multi_destroy", None, [C.c_void_p]),
+    ("sqt_multi_last_error", C.c_char_p, [C.c_void_p]),
+    ("sqt_multi_n_gpus", C.c_int, [C.c_void_p]),
+    ("sqt_multi_handle", C.c_void_p, [C.c_void_p, C.c_int]),
+    ("sqt_multi_set_limit", C.c_int, [C.c_void_p, C.c_int]),
+    ("sqt_multi_begin_file", C.c_int, [C.c_void_p]),
+    ("sqt_multi_stage_acquire", C.c_void_p, [C.c_void_p, C.c_int]),
+    ("sqt_multi_push_frame", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]),
+    ("sqt_multi_fetch_results", C.c_int, [C.c_void_p, C.POINTER(SqtResults)]),
+    ("sqt_multi_finish", C.c_int, [C.c_void_p, C.POINTER(SqtResults)]),
+    ("sqt_multi_sync", C.c_int, [C.c_void_p]),
+    ("sqt_multi_kernel_launches", C.c_longlong, [C.c_void_p]),
     ("sqt_synth_create", C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_ulonglong, C.POINTER(C.c_void_p)]),
     ("sqt_synth_next", C.c_void_p, [C.c_void_p]),
     ("sqt_synth_box_length", C.c_double, [C.c_void_p]),
@@ -110,9 +127,12 @@ HOST_API = [
     ("sqt_reader_next_header", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
     ("sqt_reader_read_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("sqt_reader_skip_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
+    ("sqt_reader_read_atoms_v", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)] + [C.c_void_p] * 6),
     ("sqt_host_factor_dr", None, [C.POINTER(SqtResults), C.c_double, C.c_void_p]),
     ("sqt_host_normalise", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int]),
     ("sqt_host_print_process", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    ("sqt_host_normalise_v", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("sqt_host_print_process_v", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),
     ("sqt_analysis_load", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p, C.c_char_p, C.c_int]),
     ("sqt_analysis_from_results", C.c_int, [C.POINTER(SqtAnalysis), C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int]),
     ("sqt_analysis_time", C.c_int, [C.POINTER(SqtAnalysis), C.c_int, C.c_double, C.c_char_p]),

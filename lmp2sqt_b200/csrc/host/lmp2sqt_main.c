@@ -4,8 +4,11 @@
  * two-pass file handling and limitCorrAv bookkeeping as the reference's main (lmp2sqt.c:117-336);
  * the per-frame work goes through the C-ABI of include/sqt.h to the GPU engine.
  *
- * Out of scope here: -s (stress), -V (velocity), -M (magnet)
- * are rejected with a message instead of silently computing something else.
+ * -V (velocity / current correlators, lmp2sqt.c:172) is served too; -s (stress) and -M (magnet) are outside the hot
+ * path and are rejected with a message instead of silently computing something else.
+ *
+ * Extension: `-g N` (or SQT_GPUS=N) shards every frame by particle over N GPUs of this box (devices SQT_DEVICE ..
+ * SQT_DEVICE + N - 1): one reader thread, one pinned frame, N asynchronous chunk copies.
  */
 #include "../../../include/sqt.h"
 #include "../../../include/sqt_host.h"
@@ -22,19 +25,21 @@
 #define M_PI 3.14159265358979323846
 #endif
 
-static void die_engine(sqt_handle *h, const char *what, int rc)
+static void die_engine(sqt_multi *m, const char *what, int rc)
 {
-	fprintf(stderr, "%s failed (%d): %s\n", what, rc, sqt_last_error(h));
+	fprintf(stderr, "%s failed (%d): %s\n", what, rc, sqt_multi_last_error(m));
 	exit(1);
 }
 
 int main(int argc, char **argv)
 {
-	bool flag_f = false, flag_F = false, flag_t = false, flag_d = false;
+	bool flag_f = false, flag_F = false, flag_t = false, flag_d = false, flag_V = false;
 	char inputFilename[512] = "in.lmp2sqt"; /* lmp2sqt.c:108 */
-	int device = 0;
+	int device = 0, n_gpus = 1;
 	const char *dev_env = getenv("SQT_DEVICE");
 	if (dev_env && *dev_env) device = atoi(dev_env);
+	const char *gpus_env = getenv("SQT_GPUS");
+	if (gpus_env && *gpus_env) n_gpus = atoi(gpus_env);
 
 	char help_message[2000];
 	snprintf(help_message, sizeof(help_message),
@@ -45,14 +50,15 @@ int main(int argc, char **argv)
 	         "			space-time, twotime, stress etc...\n"
 	         "		-t) only twotime correlation \n"
 	         "		-s) only twotime correlation + stress tensor   [not available in the B200 build]\n"
-	         "		-V) velocity correlation                        [not available in the B200 build]\n"
+	         "		-V) velocity correlation \n"
 	         "		-M) magnet correlation                          [not available in the B200 build]\n"
 	         "		-d) Get Amount of dynamic memory allocation \n"
-	         "   -i) argment filename for input variable \n",
+	         "   -i) argment filename for input variable \n"
+	         "   -g) number of GPUs of this box to shard the particles over   [B200 build only; default 1 or $SQT_GPUS]\n",
 	         argv[0]);
 	if (argc < 2) { puts(help_message); return EXIT_FAILURE; }
 	for (;;) {
-		int opt = getopt(argc, argv, "tfFsVMi:d");
+		int opt = getopt(argc, argv, "tfFsVMi:dg:");
 		if (opt == -1) break;
 		switch (opt) {
 		case 't': puts("flag_t on : two time correlation"); flag_t = true; break;
@@ -67,8 +73,10 @@ int main(int argc, char **argv)
 			snprintf(inputFilename, sizeof(inputFilename), "%s", optarg);
 			printf("intput filename : %s\n", inputFilename);
 			break;
-		case 's': case 'V': case 'M':
-			fprintf(stderr, "option -%c (stress / velocity / magnet correlators) is outside the B200 hot path; use the reference build for it\n", opt);
+		case 'V': puts("flag_velocity on :  velocity correlation "); flag_V = true; break; /* lmp2sqt.c:171-174 */
+		case 'g': n_gpus = atoi(optarg); break;
+		case 's': case 'M':
+			fprintf(stderr, "option -%c (stress / magnet correlators) is outside the B200 hot path; use the reference build for it\n", opt);
 			return EXIT_FAILURE;
 		default: puts(help_message); return EXIT_FAILURE;
 		}
@@ -83,18 +91,29 @@ int main(int argc, char **argv)
 		exit(1);
 	}
 	int limitCorrAv = deck.limitCorrAv; /* NB: the reference zeroes the global first (:125) and GetNameList then loads the deck value */
+	if (n_gpus < 1) n_gpus = 1;
+	{ /* before anything is counted or the deck rewritten: what the kernels cannot serve is refused here, with a message */
+		const int max_s = flag_V ? SQT_MAX_NCSPATIAL_V : SQT_MAX_NCSPATIAL;
+		if (deck.nCSpatial > max_s) {
+			fprintf(stderr, "nCSpatial %d is beyond what the B200 kernels cover (%d%s); use the reference build for this deck\n",
+			        deck.nCSpatial, max_s, flag_V ? " with -V" : "");
+			exit(1);
+		}
+	}
 
 	/* ---- count pass, lmp2sqt.c:200-250 ---- */
 	bool *files_on = (bool *)calloc(argc + 3, sizeof(bool));
 	long *num_data = (long *)calloc(argc + 3, sizeof(long));
+	/* one reader per input file for both passes: the count pass indexes the atom blocks (line starts), the parse pass
+	 * reuses that index after a rewind instead of scanning every block for newlines a second time */
+	sqt_reader **readers = (sqt_reader **)calloc(argc + 3, sizeof(sqt_reader *));
 	int runable = 0, full_n_snaps = 0;
 	for (int a = optind; a < argc; a++) {
-		sqt_reader *rd = sqt_reader_open(argv[a], 0);
+		sqt_reader *rd = readers[a] = sqt_reader_open(argv[a], 0);
 		if (!rd) { fprintf(stderr, "Can`t open file (%s)!!\n", argv[a]); continue; }
 		int n_snap = 0;
 		sqt_frame_header hd;
 		while (sqt_reader_next_header(rd, &hd) && hd.n_atoms > 0 && sqt_reader_skip_atoms(rd, &hd)) n_snap++;
-		sqt_reader_close(rd);
 		if (n_snap < 5) {
 			fprintf(stderr, "The # of snap is too small(<5) \n, or this file is not valid \nWe would  not use 	this file(%s)!!\n", argv[a]);
 		} else if (deck.nCBuffer < 1 || floor((n_snap - deck.nCTime) / (deck.nCTime / deck.nCBuffer)) < 1) {
@@ -120,14 +139,14 @@ int main(int argc, char **argv)
 	prm.kVal = deck.kVal; prm.deltaT = deck.deltaT; prm.mass = deck.mass; prm.rVal = deck.rVal;
 	prm.limitCorrAv = limitCorrAv; prm.nCBuffer = deck.nCBuffer; prm.nCSpatial = deck.nCSpatial; prm.nCTime = deck.nCTime;
 	prm.nCSkip = deck.nCSkip; prm.flag_f = flag_f; prm.flag_F = flag_F; prm.flag_t = flag_t; prm.device = device;
+	prm.n_gpus = n_gpus; prm.flag_V = flag_V;
 	if (deck.nCBuffer > deck.nCTime) { fputs("Error nCBuffer> nCTime\n", stderr); exit(1); }
 
 	if (flag_d) { /* AmountAllocArray, lmp2sqt.c:1658-1820: report and stop */
-		sqt_reader *rd = sqt_reader_open(argv[optind], 1);
+		sqt_reader *rd = readers[optind];
 		sqt_frame_header hd;
 		long long n = 0;
-		if (rd && sqt_reader_next_header(rd, &hd)) n = hd.n_atoms;
-		sqt_reader_close(rd);
+		if (rd) { sqt_reader_rewind(rd); if (sqt_reader_next_header(rd, &hd)) n = hd.n_atoms; }
 		int B = deck.nCBuffer < 1 ? 1 : deck.nCBuffer;
 		long long ring = 3LL * ((B + 15) / 16 * 16) * n * 8;
 		long long bufs = (long long)B * deck.nCTime * deck.nCSpatial * (8 + 8 + 4) + 14LL * deck.nCSpatial * deck.nCTime * 8;
@@ -137,9 +156,9 @@ int main(int argc, char **argv)
 		exit(1);
 	}
 
-	sqt_handle *h = NULL;
-	int rc = sqt_create(&prm, &h);
-	if (rc) die_engine(NULL, "sqt_create", rc);
+	sqt_multi *h = NULL;
+	int rc = sqt_multi_create(&prm, &h);
+	if (rc) die_engine(NULL, "sqt_multi_create", rc);
 	sqt_results res;
 	if (sqt_results_alloc(&res, deck.nCSpatial, deck.nCTime)) { fputs("Reserving memory Error!!!!!!\n", stdout); exit(1); }
 
@@ -147,8 +166,10 @@ int main(int argc, char **argv)
 	double kVal = deck.kVal;
 	for (int a = optind; a < argc; a++) {
 		if (!files_on[a]) continue;
-		sqt_reader *rd = sqt_reader_open(argv[a], 0);
-		sqt_begin_file(h); /* InitSpacetimeCorr, :282 */
+		sqt_reader *rd = readers[a];
+		if (!rd) continue;
+		sqt_reader_rewind(rd);
+		sqt_multi_begin_file(h); /* InitSpacetimeCorr, :282 */
 		sqt_frame_header hd;
 		if (sqt_reader_next_header(rd, &hd)) { /* Init_reciprocal_space, :2171-2202 (message only: kVal is reset per frame) */
 			double L0 = hd.xhi - hd.xlo;
@@ -162,15 +183,22 @@ int main(int argc, char **argv)
 		fprintf(stderr, "FULL_SNAPS = %5d\n", full_n_snaps);
 		for (long ns = 0; ns < num_data[a]; ns++) {
 			if (!sqt_reader_next_header(rd, &hd)) break;
-			double *stage = sqt_stage_acquire(h, hd.n_atoms);
+			double *stage = sqt_multi_stage_acquire(h, hd.n_atoms);
 			if (!stage) die_engine(h, "sqt_stage_acquire", -1);
-			if (!sqt_reader_read_atoms(rd, &hd, stage, stage + hd.n_atoms, stage + 2 * (size_t)hd.n_atoms)) break;
-			rc = sqt_push_frame(h, stage, hd.n_atoms, hd.n_atoms, hd.xlo, hd.xhi); /* EvalSpacetimeCorr, :300 */
+			const size_t na = (size_t)hd.n_atoms;
+			if (flag_V && hd.style != 1) {
+				/* the reference correlates whatever malloc left in Atom.vx for such dumps (snapshot.c:426-437) */
+				fprintf(stderr, "-V needs dumps written as `id type xu yu zu vx vy vz` (file %s)\n", argv[a]);
+				exit(1);
+			}
+			if (!sqt_reader_read_atoms_v(rd, &hd, stage, stage + na, stage + 2 * na, flag_V ? stage + 3 * na : NULL,
+			                             flag_V ? stage + 4 * na : NULL, flag_V ? stage + 5 * na : NULL)) break;
+			rc = sqt_multi_push_frame(h, stage, hd.n_atoms, hd.xlo, hd.xhi); /* EvalSpacetimeCorr, :300 */
 			if (rc < 0) die_engine(h, "sqt_push_frame", rc);
 			if (rc == SQT_FLUSH) { /* PrintProcess from AccumSpacetimeCorr, :438-440 */
-				rc = sqt_fetch_results(h, &res);
+				rc = sqt_multi_fetch_results(h, &res);
 				if (rc) die_engine(h, "sqt_fetch_results", rc);
-				if (sqt_host_print_process(NULL, &res, &deck, flag_f, flag_F, flag_t, NULL)) { perror("PrintProcess"); exit(1); }
+				if (sqt_host_print_process_v(NULL, &res, &deck, flag_f, flag_F, flag_t, flag_V, NULL)) { perror("PrintProcess"); exit(1); }
 			}
 			full_n_snaps_index++;
 			int new_progress = (int)(10000.0 * full_n_snaps_index / full_n_snaps);
@@ -181,18 +209,20 @@ int main(int argc, char **argv)
 				fflush(stderr);
 			}
 		}
-		sqt_reader_close(rd);
 		fprintf(stderr, "\nEnd : file : %s\n", argv[a]);
 	}
-	rc = sqt_finish(h, &res);
+	rc = sqt_multi_finish(h, &res);
 	if (rc < 0) die_engine(h, "sqt_finish", rc);
 	if (rc == 1) { /* lmp2sqt.c:327-333 */
 		fprintf(stderr, "limit corr  = %d, countCorrAv = %d\n", limitCorrAv, res.countCorrAv);
-		if (sqt_host_print_process(NULL, &res, &deck, flag_f, flag_F, flag_t, NULL)) { perror("PrintProcess"); exit(1); }
+		if (sqt_host_print_process_v(NULL, &res, &deck, flag_f, flag_F, flag_t, flag_V, NULL)) { perror("PrintProcess"); exit(1); }
 	}
-	fprintf(stderr, "engine: %s; %lld kernel launches\n", sqt_kernel_config(h), sqt_kernel_launches(h));
+	fprintf(stderr, "engine: %d GPU%s; %s; %lld kernel launches\n", sqt_multi_n_gpus(h), sqt_multi_n_gpus(h) > 1 ? "s, particle-sharded" : "",
+	        sqt_kernel_config(sqt_multi_handle(h, 0)), sqt_multi_kernel_launches(h));
 	sqt_results_free(&res);
-	sqt_destroy(h);
+	sqt_multi_destroy(h);
+	for (int a = optind; a < argc; a++) sqt_reader_close(readers[a]);
+	free(readers);
 	free(files_on);
 	free(num_data);
 	return 0;

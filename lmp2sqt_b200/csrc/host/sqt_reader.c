@@ -127,7 +127,7 @@ static int lb_next_header(sqt_reader *r, sqt_frame_header *hd)
 }
 
 /* walks the frame's chunks; with x != NULL scatters the coordinate columns into SoA.  1 ok / 0 short or inconsistent file */
-static int lb_walk_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z)
+static int lb_walk_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz)
 {
 	lb_cur c = { r->base + r->lb_chunks, r->base + r->size, 1 };
 	const int so = r->lb_size_one, cx = r->lb_col[0], cy = r->lb_col[1], cz = r->lb_col[2];
@@ -148,6 +148,11 @@ static int lb_walk_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, d
 				memcpy(&x[row0 + i], row + 8 * cx, 8);
 				memcpy(&y[row0 + i], row + 8 * cy, 8);
 				memcpy(&z[row0 + i], row + 8 * cz, 8);
+				if (vx) { /* `id type xu yu zu vx vy vz`: the three fields after zu */
+					memcpy(&vx[row0 + i], row + 8 * (cz + 1), 8);
+					memcpy(&vy[row0 + i], row + 8 * (cz + 2), 8);
+					memcpy(&vz[row0 + i], row + 8 * (cz + 3), 8);
+				}
 			}
 		}
 		lb_skip(&c, (size_t)n * 8);
@@ -270,7 +275,7 @@ static inline const char *fast_real(const char *p, const char *lim, double *out)
 	return p;
 }
 
-static inline const char *fast_line(const char *p, const int extra, double *x, double *y, double *z)
+static inline const char *fast_line(const char *p, const int extra, double *x, double *y, double *z, double *v3)
 {
 	const char *lim = p + FAST_SCAN;
 #define SKIP_SPACES while (*p == ' ' && p < lim) p++
@@ -295,6 +300,18 @@ static inline const char *fast_line(const char *p, const int extra, double *x, d
 		if (*p == '\n') return p + 1;
 		if (p >= lim) return NULL;
 		const char *nl = (const char *)memchr(p, '\n', 128); /* trailing blanks or \r */
+		return nl ? nl + 1 : NULL;
+	}
+	if (v3) { /* -V: the three columns after zu are vx vy vz (8-column style only, snapshot.c:285-300) */
+		const char *q = p;
+		for (int k = 0; k < 3; k++) {
+			if (*q != ' ') return NULL;
+			while (*q == ' ' && q < lim) q++;
+			if (!(q = fast_real(q, lim, &v3[k]))) return NULL;
+		}
+		if (*q == '\n') return q + 1;
+		if (q >= lim) return NULL;
+		const char *nl = (const char *)memchr(q, '\n', 128);
 		return nl ? nl + 1 : NULL;
 	}
 	/* wider styles (vx vy vz / mux muy muz): the columns are not used, but the reference parses them -- a line that lacks
@@ -486,7 +503,7 @@ int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd)
 {
 	size_t endp;
 	if (hd->n_atoms <= 0) return 1;
-	if (r->raw == 2) return lb_walk_atoms(r, hd, NULL, NULL, NULL);
+	if (r->raw == 2) return lb_walk_atoms(r, hd, NULL, NULL, NULL, NULL, NULL, NULL);
 	if (r->raw) { r->pos += (size_t)hd->n_atoms * 24; return 1; }
 	const int n = hd->n_atoms;
 	const size_t nm = ((size_t)n + MARK_LINES - 1) / MARK_LINES;
@@ -514,9 +531,17 @@ int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd)
 
 int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z)
 {
+	return sqt_reader_read_atoms_v(r, hd, x, y, z, NULL, NULL, NULL);
+}
+
+int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz)
+{
 	const int n = hd->n_atoms;
 	if (n <= 0) return 1;
-	if (r->raw == 2) return lb_walk_atoms(r, hd, x, y, z);
+	/* velocities exist only in the 8-column style: the reference's test for the 11-column header is shadowed by its
+	 * 8-column dipole prefix test (snapshot.c:262-283), and the raw frame file carries coordinates only */
+	if (vx && (hd->style != 1 || r->raw == 1)) { r->pos = r->size; return 0; }
+	if (r->raw == 2) return lb_walk_atoms(r, hd, x, y, z, vx, vy, vz);
 	if (r->raw) { /* already SoA: three straight copies into the staging buffer */
 		const char *src = r->base + r->pos;
 		memcpy(x, src, (size_t)n * 8); memcpy(y, src + (size_t)n * 8, (size_t)n * 8); memcpy(z, src + (size_t)n * 16, (size_t)n * 8);
@@ -556,8 +581,13 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 		} else pos = starts[t];
 		for (int i = i0; i < i1; i++) {
 			if (r->size - pos > FAST_MARGIN) { /* far enough from the end of the mapping for the unchecked scan */
-				const char *nx = fast_line(r->base + pos, extra, &x[i], &y[i], &z[i]);
-				if (nx) { pos = (size_t)(nx - r->base); continue; }
+				double v3[3];
+				const char *nx = fast_line(r->base + pos, extra, &x[i], &y[i], &z[i], vx ? v3 : NULL);
+				if (nx) {
+					if (vx) { vx[i] = v3[0]; vy[i] = v3[1]; vz[i] = v3[2]; }
+					pos = (size_t)(nx - r->base);
+					continue;
+				}
 			}
 			const char *p, *e;
 			if (!take_line(r, &pos, &p, &e)) { bad |= 2; break; }
@@ -567,8 +597,13 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 			x[i] = tok_real(&c, e, &ok);
 			y[i] = tok_real(&c, e, &ok);
 			z[i] = tok_real(&c, e, &ok);
-			for (int k = extra; k > 0; k--)
-				if (!tok_skip(&c, e)) ok = 0;              /* unused columns of the wider styles must be there too */
+			if (vx) {
+				vx[i] = tok_real(&c, e, &ok);
+				vy[i] = tok_real(&c, e, &ok);
+				vz[i] = tok_real(&c, e, &ok);
+			} else
+				for (int k = extra; k > 0; k--)
+					if (!tok_skip(&c, e)) ok = 0;          /* unused columns of the wider styles must be there too */
 			if (!ok && i != n - 1) bad |= 1; /* a short line fails the frame unless it is the last (snapshot.c:352-356) */
 		}
 	}

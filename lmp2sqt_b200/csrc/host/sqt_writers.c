@@ -42,6 +42,11 @@ void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr)
 
 void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t)
 {
+	sqt_host_normalise_v(r, d, flag_f, flag_F, flag_t, 0);
+}
+
+void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V)
+{
 	const int S = r->nCSpatial, T = r->nCTime;
 	const double N = (double)r->nPtls;
 	const double inverseNptls = 1. / N;
@@ -57,6 +62,13 @@ void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_
 				av[q][e] = average;
 				sd[q][e] = sqrt((averageSq - average * average));
 			}
+		if (flag_V) { /* lmp2sqt.c:607-611 */
+			double *c2[3] = { r->avC2_v_rho, r->avC2_rho_v, r->avC2_v_v };
+			for (int q = 0; q < 3; q++)
+				for (int e = 0; e < S * T; e++) c2[q][e] *= inverseNptls * average_number;
+		}
+		/* The table is only ever filled under -t (EvalTwoTimeEach as a whole is `if (flag_t)`, lmp2sqt.c:1370): the engine
+		 * leaves it zero otherwise, and scaling zeros is what the reference does then (:625-630) */
 		double *factorDr = (double *)malloc(sizeof(double) * S);
 		sqt_host_factor_dr(r, d->rVal, factorDr);
 		for (int nt = 1; nt < T; nt++) /* lag 0 is left unscaled, lmp2sqt.c:626 */
@@ -66,10 +78,16 @@ void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_
 	if (flag_t) {
 		const double scale_factor = 1. / (N * r->countCorrAv);
 		const double factor_msdcm = 1. / (r->countCorrAv);
+		const double factor_Cvv = 1. / (N * r->countCorrAv * 3.);      /* lmp2sqt.c:642-644 */
+		const double factor_Cvcmvcm = 1. / (r->countCorrAv * 3.);
 		for (int nt = 0; nt < T; nt++) {
 			r->rrMSDAv[nt] *= scale_factor;
 			r->rrMSDCMAv[nt] *= factor_msdcm;
 			r->rrMQDAv[nt] *= scale_factor;
+			if (flag_V) {
+				r->rrCvvAv[nt] *= factor_Cvv;
+				r->rrCvcmvcmAv[nt] *= factor_Cvcmvcm;
+			}
 		}
 	}
 }
@@ -134,18 +152,36 @@ static void write_binary(FILE *fp, const sqt_results *r, const sqt_deck *d, int 
 }
 
 /* PrintEtc, lmp2sqt.c:865-1093 (SSF and Dt; the C2_* and Stress files belong to -V/-M/-s) */
-static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, int flag_f, int flag_t, const char *date)
+static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, int flag_f, int flag_t, int flag_V, const char *date)
 {
 	const int S = r->nCSpatial, T = r->nCTime;
-	char name[64], fn_Dt[512], fn_SSF[512];
+	char name[64], fn_Dt[512], fn_SSF[512], fn_C2[3][512];
+	static const char *c2_name[3] = { "C2_v_rho", "C2_rho_v", "C2_v_v" };
 	int nfile = 0;
 	do { /* first unused index, probed on the Dt name only (lmp2sqt.c:886-902) */
 		snprintf(name, sizeof(name), "Dt%03d.info.%s", nfile, date);
 		join(fn_Dt, sizeof(fn_Dt), dir, name);
 		snprintf(name, sizeof(name), "SSF%03d.info.%s", nfile, date);
 		join(fn_SSF, sizeof(fn_SSF), dir, name);
+		for (int q = 0; q < 3; q++) {
+			snprintf(name, sizeof(name), "%s%03d.info.%s", c2_name[q], nfile, date);
+			join(fn_C2[q], sizeof(fn_C2[q]), dir, name);
+		}
 		nfile++;
 	} while (0 == access(fn_Dt, F_OK));
+	if (flag_f && flag_V) { /* lmp2sqt.c:933-993: one row per lag, "%7.3f" time then " %8.4e" per nk */
+		const double *c2[3] = { r->avC2_v_rho, r->avC2_rho_v, r->avC2_v_v };
+		for (int q = 0; q < 3; q++) {
+			FILE *fp = fopen(fn_C2[q], "w");
+			if (!fp) return -1;
+			for (int nt = 0; nt < T; nt++) {
+				fprintf(fp, "%7.3f", nt * 1. * d->deltaT);
+				for (int nk = 0; nk < S; nk++) fprintf(fp, " %8.4e", c2[q][nk * T + nt]);
+				fprintf(fp, "\n");
+			}
+			fclose(fp);
+		}
+	}
 	if (flag_f) {
 		FILE *fp = fopen(fn_SSF, "w");
 		if (!fp) return -1;
@@ -160,6 +196,7 @@ static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, i
 		FILE *fp = fopen(fn_Dt, "w");
 		if (!fp) return -1;
 		fprintf(fp, "#time MSD msdx msdy msdz D(t) anotherform MQD");
+		if (flag_V) fprintf(fp, " Cvv Cvcmvcm");
 		fprintf(fp, " MSDCM\n");
 		fprintf(stderr, "print time correlation \n");
 		double *rrDt = (double *)calloc(T > 3 ? T : 3, sizeof(double));
@@ -176,6 +213,7 @@ static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, i
 			if (nt != 0) anotherDt = msd[nt] / (tVal * DIM * 2);
 			fprintf(fp, "%8.4f %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g", tVal, msd[nt], 0., 0., 0., rrDt[nt], anotherDt,
 			        r->rrMQDAv[nt]);
+			if (flag_V) fprintf(fp, " %8.4f %8.4g", r->rrCvvAv[nt], r->rrCvcmvcmAv[nt]);
 			fprintf(fp, " %8.4f\n", r->rrMSDCMAv[nt]);
 		}
 		free(rrDt);
@@ -187,6 +225,12 @@ static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, i
 int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t,
                            const char *date)
 {
+	return sqt_host_print_process_v(dir, r, d, flag_f, flag_F, flag_t, 0, date);
+}
+
+int sqt_host_print_process_v(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V,
+                             const char *date)
+{
 	char today[32], path[512];
 	if (!date) {
 		time_t raw = time(NULL);
@@ -197,8 +241,8 @@ int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, i
 	FILE *flog = fopen(path, "w+");
 	if (!flog) return -1;
 	fputs("Call PrintProcess : \n", flog);
-	sqt_host_normalise(r, d, flag_f, flag_F, flag_t);
-	if (write_etc(dir, r, d, flag_f, flag_t, date)) { fclose(flog); return -1; }
+	sqt_host_normalise_v(r, d, flag_f, flag_F, flag_t, flag_V);
+	if (write_etc(dir, r, d, flag_f, flag_t, flag_V, date)) { fclose(flog); return -1; }
 	if (flag_f) {
 		const char *fout_filename = "output.binary";
 		join(path, sizeof(path), dir, fout_filename);

@@ -23,7 +23,9 @@ struct sqt_handle {
 	int S, T, B;
 	int device, n_sm;
 	char err[512];
-	char cfg[512];
+	char cfg[768];
+	bool flag_f, flag_F, flag_t, flag_V;
+	int ncomp;                // arrays per frame: 3 (x y z) or 6 (+ vx vy vz with -V)
 
 	// ---- ring bookkeeping (host mirror of TBuf.count etc.) ----
 	int limitCorrAv, countCorrAv, n_print;
@@ -32,7 +34,7 @@ struct sqt_handle {
 	std::vector<double> h_invL0;
 	long long nPtls;
 	int n_local;
-	bool sized, first_done;
+	bool sized, first_done, broken;
 	double L, vol, kVal, first_vol;
 	int first_limit;
 
@@ -52,11 +54,13 @@ struct sqt_handle {
 	int *d_hist_cur, *d_bufHist;
 	double *d_bufFs, *d_bufF, *d_bufMSD, *d_bufMQD, *d_bufMSDCM;
 	double *d_rho0, *d_sumr0, *d_invL0, *d_rho_cur, *d_cblk;
+	int rho_n;                // 6 nCS + 3: one block of d_rho_cur (rho + sum r; with -V a second block kvel + sum v follows)
 	long long *d_thr;
-	double *d_avblk, *d_latblk; // [7*S*T + 3*T]
+	double *d_avblk, *d_latblk; // [10*S*T + 5*T]
 	size_t avblk_n;
 	bool latched;
 	int latched_count, latched_limit;
+	int self_kind;            // which kernel serves the per-particle terms: SELF_NONE / SELF_MMA / SELF_VEC / SELF_CLASSIC
 	KernelChoice kc;
 	MmaChoice mc;             // blocked-Chebyshev / DMMA path for the real slots (large nCSpatial)
 	double *d_mma_partial;
@@ -65,15 +69,20 @@ struct sqt_handle {
 	double *d_rho_partial;
 	double *d_mma_extra, *d_rho_extra; // per-warp sums kept outside the DMMA product (MmaChoice.SPOUT)
 	int *d_mma_ctr;
-	cudaStream_t s_main, s_copy, s_coll;
-	cudaEvent_t ev_red, ev_coll, ev_t0, ev_t1;
-	bool coll_pending;
+	// -V
+	double *d_vring, *d_vpartial, *d_bufC2, *d_bufCvv, *d_bufCvcm, *d_kvel0, *d_sumv0;
+	int vel_nchunk, vel_chunk;
+	cudaStream_t s_main, s_copy, s_coll, s_aux;
+	cudaEvent_t ev_red, ev_coll, ev_rho, ev_rhoc, ev_prod, ev_t0, ev_t1;
+	bool coll_pending, rhoc_pending;
 	SqtComm *comm;
 	int rank, nranks;
 	long long launches;
 	bool prof;
-	std::vector<cudaEvent_t> prof_ev; // pairs
+	std::vector<cudaEvent_t> prof_pool; // pairs, pre-created by sqt_profile_enable so that the timed loop creates nothing
+	size_t prof_used;
 };
+enum { SELF_NONE = 0, SELF_MMA = 1, SELF_VEC = 2, SELF_CLASSIC = 3 };
 
 static int fail(sqt_handle *h, int code, const char *fmt, ...)
 {
@@ -97,10 +106,11 @@ extern "C" int sqt_results_alloc(sqt_results *r, int S, int T)
 	if (!r || S < 1 || T < 1) return SQT_ERR_ARG;
 	memset(r, 0, sizeof(*r));
 	r->nCSpatial = S; r->nCTime = T;
-	double **a2[7] = { &r->avF_qq2, &r->StdDevF_qq2, &r->avF_s_qq2, &r->StdDevF_s_qq2, &r->avF_d_qq2, &r->StdDevF_d_qq2, &r->avDrTable };
-	double **a1[3] = { &r->rrMSDAv, &r->rrMQDAv, &r->rrMSDCMAv };
-	for (int i = 0; i < 7; ++i) if (!(*a2[i] = (double *)calloc((size_t)S * T, sizeof(double)))) return SQT_ERR_NOMEM;
-	for (int i = 0; i < 3; ++i) if (!(*a1[i] = (double *)calloc(T, sizeof(double)))) return SQT_ERR_NOMEM;
+	double **a2[10] = { &r->avF_qq2, &r->StdDevF_qq2, &r->avF_s_qq2, &r->StdDevF_s_qq2, &r->avF_d_qq2, &r->StdDevF_d_qq2, &r->avDrTable,
+	                    &r->avC2_v_rho, &r->avC2_rho_v, &r->avC2_v_v };
+	double **a1[5] = { &r->rrMSDAv, &r->rrMQDAv, &r->rrMSDCMAv, &r->rrCvvAv, &r->rrCvcmvcmAv };
+	for (int i = 0; i < 10; ++i) if (!(*a2[i] = (double *)calloc((size_t)S * T, sizeof(double)))) return SQT_ERR_NOMEM;
+	for (int i = 0; i < 5; ++i) if (!(*a1[i] = (double *)calloc(T, sizeof(double)))) return SQT_ERR_NOMEM;
 	return SQT_OK;
 }
 
@@ -110,6 +120,7 @@ extern "C" void sqt_results_free(sqt_results *r)
 	free(r->avF_qq2); free(r->StdDevF_qq2); free(r->avF_s_qq2); free(r->StdDevF_s_qq2);
 	free(r->avF_d_qq2); free(r->StdDevF_d_qq2); free(r->avDrTable);
 	free(r->rrMSDAv); free(r->rrMQDAv); free(r->rrMSDCMAv);
+	free(r->avC2_v_rho); free(r->avC2_rho_v); free(r->avC2_v_v); free(r->rrCvvAv); free(r->rrCvcmvcmAv);
 	memset(r, 0, sizeof(*r));
 }
 
@@ -136,6 +147,10 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	sqt_handle *h = nullptr;
 	if (!p || !out) return fail(h, SQT_ERR_ARG, "sqt_create: null argument");
 	if (p->nCSpatial < 1 || p->nCTime < 1) return fail(h, SQT_ERR_ARG, "sqt_create: nCSpatial and nCTime must be >= 1");
+	if (p->nCSpatial > SQT_MAX_NCSPATIAL)
+		return fail(h, SQT_ERR_ARG, "sqt_create: nCSpatial %d is beyond what the kernels cover (%d)", p->nCSpatial, SQT_MAX_NCSPATIAL);
+	if (p->flag_V && p->nCSpatial > SQT_MAX_NCSPATIAL_V)
+		return fail(h, SQT_ERR_ARG, "sqt_create: -V needs nCSpatial <= %d (got %d)", SQT_MAX_NCSPATIAL_V, p->nCSpatial);
 	if (!(p->rVal > 0)) return fail(h, SQT_ERR_ARG, "sqt_create: rVal must be > 0");
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -151,21 +166,33 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	if (h->B > h->T) h->B = h->T; // GetNameList tail, lmp2sqt.c:2105
 	if (h->B < 1) h->B = 1;       // main, lmp2sqt.c:240-242
 	h->device = p->device;
+	h->flag_F = p->flag_F != 0;
+	h->flag_f = p->flag_f != 0 || h->flag_F; // -F switches -f on as well (lmp2sqt.c:160-165)
+	h->flag_t = p->flag_t != 0;
+	h->flag_V = p->flag_V != 0;
+	h->ncomp = h->flag_V ? 6 : 3;
 	h->limitCorrAv = p->limitCorrAv;
 	h->countCorrAv = 0; h->n_print = 0; h->nSkip = 0; h->p_file = 0;
 	h->count.assign(h->B, 0);
 	h->h_invL0.assign(h->B, 0.0);
-	h->nPtls = 0; h->n_local = 0; h->sized = false; h->first_done = false;
+	h->nPtls = 0; h->n_local = 0; h->sized = false; h->first_done = false; h->broken = false;
 	h->L = h->vol = h->first_vol = 0; h->kVal = p->kVal; h->first_limit = 0;
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
-	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr; h->mc.on = 0; h->mc.geo = 0; h->vc.on = 0; h->rmc.on = 0; h->d_rho_partial = nullptr; h->d_mma_extra = h->d_rho_extra = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
+	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr;
+	h->mc.on = 0; h->mc.geo = 0; h->vc.on = 0; h->rmc.on = 0; h->self_kind = SELF_NONE;
+	h->d_rho_partial = nullptr; h->d_mma_extra = h->d_rho_extra = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
 	h->d_avblk = h->d_latblk = nullptr;
+	h->d_vring = h->d_vpartial = h->d_bufC2 = h->d_bufCvv = h->d_bufCvcm = h->d_kvel0 = h->d_sumv0 = nullptr;
+	h->vel_nchunk = h->vel_chunk = 0;
 	h->latched = false; h->latched_count = 0; h->latched_limit = 0;
-	h->comm = nullptr; h->rank = 0; h->nranks = 1; h->launches = 0; h->prof = false; h->coll_pending = false;
-	h->s_main = h->s_copy = h->s_coll = nullptr;
+	h->comm = nullptr; h->rank = 0; h->nranks = 1; h->launches = 0; h->prof = false; h->prof_used = 0;
+	h->coll_pending = h->rhoc_pending = false;
+	h->s_main = h->s_copy = h->s_coll = h->s_aux = nullptr;
+	h->ev_copy[0] = h->ev_copy[1] = h->ev_ring[0] = h->ev_ring[1] = nullptr;
+	h->ev_red = h->ev_coll = h->ev_rho = h->ev_rhoc = h->ev_prod = h->ev_t0 = h->ev_t1 = nullptr;
 
 #define CUC(call)                                                                                   \
 	do {                                                                                            \
@@ -182,6 +209,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->n_sm = prop.multiProcessorCount;
 	CUC(cudaStreamCreate(&h->s_main));
 	CUC(cudaStreamCreate(&h->s_copy));
+	CUC(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking)); // result read-backs that must not wait for the self-term kernel
 	h->s_coll = h->s_main; // a separate collective stream is created when a communicator is attached
 	for (int i = 0; i < 2; ++i) {
 		CUC(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
@@ -189,6 +217,9 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	}
 	CUC(cudaEventCreateWithFlags(&h->ev_red, cudaEventDisableTiming));
 	CUC(cudaEventCreateWithFlags(&h->ev_coll, cudaEventDisableTiming));
+	CUC(cudaEventCreateWithFlags(&h->ev_rho, cudaEventDisableTiming));
+	CUC(cudaEventCreateWithFlags(&h->ev_rhoc, cudaEventDisableTiming));
+	CUC(cudaEventCreateWithFlags(&h->ev_prod, cudaEventDisableTiming));
 	CUC(cudaEventCreate(&h->ev_t0));
 	CUC(cudaEventCreate(&h->ev_t1));
 
@@ -207,10 +238,21 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	CUC(cudaMemset(h->d_sumr0, 0, sizeof(double) * B * 3));
 	CUC(cudaMalloc(&h->d_invL0, sizeof(double) * B));
 	CUC(cudaMemset(h->d_invL0, 0, sizeof(double) * B));
-	CUC(cudaMalloc(&h->d_rho_cur, sizeof(double) * (6 * S + 3)));
-	CUC(cudaMemset(h->d_rho_cur, 0, sizeof(double) * (6 * S + 3)));
-	CUC(cudaMalloc(&h->d_cblk, sizeof(double) * (2 * T * S + 2 * T)));
-	h->avblk_n = 7 * S * T + 3 * T;
+	h->rho_n = 6 * (int)S + 3;
+	CUC(cudaMalloc(&h->d_rho_cur, sizeof(double) * 3 * h->rho_n)); // rho + sum r | kvel + sum v (-V) | scratch
+	CUC(cudaMemset(h->d_rho_cur, 0, sizeof(double) * 3 * h->rho_n));
+	CUC(cudaMalloc(&h->d_cblk, sizeof(double) * (2 * T * S + 3 * T)));
+	if (h->flag_V) {
+		CUC(cudaMalloc(&h->d_bufC2, sizeof(double) * 3 * B * T * S));
+		CUC(cudaMemset(h->d_bufC2, 0, sizeof(double) * 3 * B * T * S));
+		double **vb[] = { &h->d_bufCvv, &h->d_bufCvcm };
+		for (auto pp : vb) { CUC(cudaMalloc(pp, sizeof(double) * B * T)); CUC(cudaMemset(*pp, 0, sizeof(double) * B * T)); }
+		CUC(cudaMalloc(&h->d_kvel0, sizeof(double) * B * 6 * S));
+		CUC(cudaMemset(h->d_kvel0, 0, sizeof(double) * B * 6 * S));
+		CUC(cudaMalloc(&h->d_sumv0, sizeof(double) * B * 3));
+		CUC(cudaMemset(h->d_sumv0, 0, sizeof(double) * B * 3));
+	}
+	h->avblk_n = 10 * S * T + 5 * T;
 	CUC(cudaMalloc(&h->d_avblk, sizeof(double) * h->avblk_n));
 	CUC(cudaMemset(h->d_avblk, 0, sizeof(double) * h->avblk_n)); // ZeroAvSpacetimeCorr, lmp2sqt.c:1921
 	CUC(cudaMalloc(&h->d_latblk, sizeof(double) * h->avblk_n));
@@ -226,28 +268,39 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	return SQT_OK;
 }
 
+// everything size_for_atoms allocated
+static void release_sized(sqt_handle *h)
+{
+	for (int i = 0; i < 2; ++i) { cudaFree(h->d_cur[i]); h->d_cur[i] = nullptr; }
+	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr);
+	cudaFree(h->d_rho_partial); cudaFree(h->d_mma_extra); cudaFree(h->d_rho_extra); cudaFree(h->d_vring); cudaFree(h->d_vpartial);
+	h->d_ring = h->d_partial = h->d_mma_partial = h->d_rho_partial = h->d_mma_extra = h->d_rho_extra = h->d_vring = h->d_vpartial = nullptr;
+	h->d_tile_ctr = h->d_mma_ctr = nullptr;
+	h->sized = false;
+}
+
 extern "C" void sqt_destroy(sqt_handle *h)
 {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	if (h->comm) sqt_comm_destroy(h->comm);
+	release_sized(h);
 	for (int i = 0; i < 2; ++i) {
-		cudaFree(h->d_cur[i]);
 		if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_ring[i]) cudaEventDestroy(h->ev_ring[i]);
 	}
-	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr); cudaFree(h->d_rho_partial); cudaFree(h->d_mma_extra); cudaFree(h->d_rho_extra); cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
+	cudaFree(h->d_hist_cur); cudaFree(h->d_bufHist);
 	cudaFree(h->d_bufFs); cudaFree(h->d_bufF); cudaFree(h->d_bufMSD); cudaFree(h->d_bufMQD); cudaFree(h->d_bufMSDCM);
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
-	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-	if (h->ev_red) cudaEventDestroy(h->ev_red);
-	if (h->ev_coll) cudaEventDestroy(h->ev_coll);
-	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
-	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	cudaFree(h->d_bufC2); cudaFree(h->d_bufCvv); cudaFree(h->d_bufCvcm); cudaFree(h->d_kvel0); cudaFree(h->d_sumv0);
+	for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+	cudaEvent_t evs[] = { h->ev_red, h->ev_coll, h->ev_rho, h->ev_rhoc, h->ev_prod, h->ev_t0, h->ev_t1 };
+	for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
 	if (h->s_coll && h->s_coll != h->s_main) cudaStreamDestroy(h->s_coll);
+	if (h->s_aux) cudaStreamDestroy(h->s_aux);
 	if (h->s_copy) cudaStreamDestroy(h->s_copy);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	delete h;
@@ -277,7 +330,7 @@ static int ensure_stage(sqt_handle *h, int n)
 	for (int i = 0; i < 2; ++i) {
 		if (h->copy_pending[i]) { CU(cudaEventSynchronize(h->ev_copy[i])); h->copy_pending[i] = false; }
 		if (h->h_stage[i]) { CU(cudaFreeHost(h->h_stage[i])); h->h_stage[i] = nullptr; }
-		CU(cudaMallocHost(&h->h_stage[i], sizeof(double) * 3 * (size_t)n));
+		CU(cudaMallocHost(&h->h_stage[i], sizeof(double) * h->ncomp * (size_t)n));
 	}
 	h->stage_cap = n;
 	return SQT_OK;
@@ -297,33 +350,42 @@ extern "C" double *sqt_stage_acquire(sqt_handle *h, int n_atoms_local)
 }
 
 // First processed frame: the analogue of Alloc_more (lmp2sqt.c:1926-2012) -- everything whose
-// size depends on the atom count.
-static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
+// size depends on the atom count.  On failure nothing stays allocated and the handle refuses further frames.
+static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 {
 	CU(cudaSetDevice(h->device));
 	h->n_local = n_local;
 	h->nPtls = n_total;
 	h->cur_pitch = ((long long)n_local + 31) & ~31LL;
-	for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_cur[i], sizeof(double) * 3 * h->cur_pitch));
+	for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_cur[i], sizeof(double) * h->ncomp * h->cur_pitch));
+	// Which kernel serves the per-particle terms.  F_s needs the nCSpatial Chebyshev chains (-F); MSD, MQD and the van Hove
+	// table (-t) only the displacement: without -F the particle-per-lane kernel runs with a single chain, and with neither
+	// flag nothing per-particle is computed at all (the reference does the same, lmp2sqt.c:1370, 1479, 1527).
+	const bool want_self = h->flag_F || h->flag_t;
 	int rc = sqt_pick_mma(h->S, h->B, n_local, h->n_sm, &h->mc);
 	if (rc != 0) return fail(h, SQT_ERR_CUDA, "mma kernel selection failed (rc=%d)", rc);
-	if (!h->mc.on) {
-		rc = sqt_pick_vec(h->S, h->B, n_local, h->n_sm, &h->vc);
+	if (!h->flag_F) h->mc.on = 0;
+	h->vc.on = 0;
+	if (want_self && !h->mc.on && h->mc.geo) { // (rho(k) comes from the tensor-core rho kernel on this path)
+		rc = sqt_pick_vec(h->S, h->flag_F ? h->S : 1, h->B, n_local, h->n_sm, &h->vc);
 		if (rc != 0) return fail(h, SQT_ERR_CUDA, "vector kernel selection failed (rc=%d)", rc);
-		if (h->vc.on && !h->mc.geo) h->vc.on = 0; // rho(k) comes from the tensor-core rho kernel on this path
 	}
-	const bool lane_family = h->mc.on || h->vc.on; // a particle per lane: particle-minor ring, rho(k) from rho_mma_kernel
-	// with a particle-per-lane self kernel on, the classic kernel serves at most the six virtual rho(k) slots (B = 0 for it)
-	rc = sqt_pick_kernel(h->S, lane_family ? 0 : h->B, n_local, h->n_sm, &h->kc);
+	h->self_kind = !want_self ? SELF_NONE : (h->mc.on ? SELF_MMA : (h->vc.on ? SELF_VEC : SELF_CLASSIC));
+	const bool lane_family = h->self_kind == SELF_MMA || h->self_kind == SELF_VEC; // a particle per lane: particle-minor ring
+	// the classic kernel serves its own slots only for SELF_CLASSIC; otherwise at most the six virtual rho(k) slots (B = 0 for it)
+	rc = sqt_pick_kernel(h->S, h->self_kind == SELF_CLASSIC ? h->B : 0, n_local, h->n_sm, &h->kc);
 	if (rc != 0) return fail(h, SQT_ERR_CUDA, "no ring-kernel variant for nCSpatial=%d (rc=%d)", h->S, rc);
 	h->RP = (h->B + 15) & ~15; // 128-byte rows: a warp's 32 origins of one particle/axis are contiguous
 	// the tensor-core kernel walks particles along the warp, so its ring is [slot][axis][particle] (pitch: a multiple of 32
 	// particles); the classic kernel walks slots along the warp: [particle][axis][slot]
 	h->ring_np = ((long long)n_local + 31) & ~31LL;
-	const size_t ring_bytes = lane_family ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
-	cudaError_t e = cudaMalloc(&h->d_ring, ring_bytes);
-	if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin ring of %.2f GB does not fit on the device: %s", ring_bytes / 1e9, cudaGetErrorString(e));
-	CU(cudaMemsetAsync(h->d_ring, 0, ring_bytes, h->s_main));
+	size_t ring_bytes = 0;
+	if (h->self_kind != SELF_NONE) {
+		ring_bytes = lane_family ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
+		cudaError_t e = cudaMalloc(&h->d_ring, ring_bytes);
+		if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin ring of %.2f GB does not fit on the device: %s", ring_bytes / 1e9, cudaGetErrorString(e));
+		CU(cudaMemsetAsync(h->d_ring, 0, ring_bytes, h->s_main));
+	}
 	const size_t part_bytes = sizeof(double) * (size_t)h->kc.NWSG * h->kc.KW * h->kc.NV * (32 / h->kc.G);
 	CU(cudaMalloc(&h->d_partial, part_bytes));
 	CU(cudaMemsetAsync(h->d_partial, 0, part_bytes, h->s_main));
@@ -341,6 +403,9 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 		const size_t xb = h->mc.on ? sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * 2 : 16;
 		CU(cudaMalloc(&h->d_mma_extra, xb));
 		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
+	}
+	h->rmc.on = 0;
+	if (h->self_kind != SELF_CLASSIC || h->flag_V) {
 		const char *rm = getenv("SQT_RHO_MMA");
 		if (!(rm && *rm == '0')) {
 			rc = sqt_pick_rho_mma(h->mc, n_local, h->n_sm, &h->rmc);
@@ -353,28 +418,90 @@ static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
 			mma_bytes += rb;
 		}
 	}
+	if (h->flag_V) {
+		if (!h->rmc.on) return fail(h, SQT_ERR_ARG, "-V needs the tensor-core rho(k) kernel (nCSpatial <= %d, SQT_MMA / SQT_RHO_MMA not 0)", SQT_MAX_NCSPATIAL_V);
+		if (h->flag_t) {
+			const size_t vb = sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np;
+			cudaError_t e = cudaMalloc(&h->d_vring, vb);
+			if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin-velocity ring of %.2f GB does not fit on the device: %s", vb / 1e9, cudaGetErrorString(e));
+			CU(cudaMemsetAsync(h->d_vring, 0, vb, h->s_main));
+			ring_bytes += vb;
+			int chunk = 8192, nch = (n_local + chunk - 1) / chunk;
+			if (nch > 2048) { nch = 2048; chunk = (n_local + nch - 1) / nch; nch = (n_local + chunk - 1) / chunk; }
+			h->vel_chunk = chunk; h->vel_nchunk = nch;
+			CU(cudaMalloc(&h->d_vpartial, sizeof(double) * (size_t)h->B * nch));
+		}
+	}
 	int off = 0;
-	if (h->vc.on)
+	if (h->self_kind == SELF_NONE)
+		off = snprintf(h->cfg, sizeof(h->cfg), "no per-particle kernel (neither -F nor -t); rho(k): ");
+	if (h->self_kind == SELF_VEC)
 		off = snprintf(h->cfg, sizeof(h->cfg),
-		               "self_ring_vec_kernel<C=%d,SPW=%d> (a particle per lane, sums in registers) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
+		               "self_ring_vec_kernel<C=%d,SPW=%d> (a particle per lane, sums in registers%s) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
 		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
-		               h->vc.C, h->vc.SPW, h->vc.blocks, h->vc.WPB * 32, h->vc.regs, h->vc.smem, h->vc.occ, h->vc.NWSG, h->vc.KW,
+		               h->vc.C, h->vc.SPW, h->flag_F ? "" : "; no -F: MSD / van Hove only", h->vc.blocks, h->vc.WPB * 32, h->vc.regs, h->vc.smem, h->vc.occ, h->vc.NWSG, h->vc.KW,
 		               h->vc.dynamic ? "dynamic" : "static", h->vc.tile);
-	if (h->mc.on)
+	if (h->self_kind == SELF_MMA)
 		off = snprintf(h->cfg, sizeof(h->cfg),
 		               "self_ring_mma_kernel<NT=%d,SPW=%d> (blocked Chebyshev S=%d on DMMA%s) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
 		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
 		               h->mc.NT, h->mc.SPW, h->mc.S, h->mc.SPOUT ? ", MSD/MQD outside" : "", h->mc.blocks, h->mc.WPB * 32, h->mc.regs, h->mc.smem, h->mc.occ, h->mc.NWSG, h->mc.KW,
 		               h->mc.dynamic ? "dynamic" : "static", h->mc.tile);
 	if (h->rmc.on)
-		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles; unused: ",
-		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ);
+		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles%s; %s: ",
+		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ, h->flag_V ? " (+ velocity-weighted pass, vel_ring_kernel)" : "",
+		                h->self_kind == SELF_CLASSIC ? "self terms" : "unused");
 	snprintf(h->cfg + off, sizeof(h->cfg) - off,
 	         "self_ring_kernel<C=%d,G=%d> persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; %d slot groups x %d warps, "
 	         "%s tiles of %d particles (%d tiles); slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB",
 	         h->kc.C, h->kc.G, h->kc.blocks, h->kc.WPB * 32, h->kc.regs, h->kc.smem, h->kc.occ, h->kc.NWSG, h->kc.KW,
 	         h->kc.dynamic ? "dynamic" : "static", h->kc.tile, h->kc.ntiles, h->B, SQT_NVIRT, ring_bytes / 1e9, (part_bytes + mma_bytes) / 1e6);
 	h->sized = true;
+	return SQT_OK;
+}
+
+static int size_for_atoms(sqt_handle *h, int n_local, long long n_total)
+{
+	const int rc = size_for_atoms_impl(h, n_local, n_total);
+	if (rc != SQT_OK) { // nothing half-allocated survives; the handle stays unusable for frames (the reference exits here, lmp2sqt.c:1651-1657)
+		cudaStreamSynchronize(h->s_main);
+		release_sized(h);
+		h->broken = true;
+	}
+	return rc;
+}
+
+static cudaEvent_t prof_event(sqt_handle *h)
+{
+	if (h->prof_used == h->prof_pool.size()) { // (only if more frames are profiled than sqt_profile_enable prepared)
+		cudaEvent_t e = nullptr;
+		cudaEventCreate(&e);
+		h->prof_pool.push_back(e);
+	}
+	return h->prof_pool[h->prof_used++];
+}
+
+// rho(k) is final on the device (and, sharded, summed over ranks): the F(q,t) part of the frame (lmp2sqt.c:1584-1586),
+// the origin copies of rho and the centre-of-mass terms.  Runs on the collective stream, which only waits for `after`.
+static int stage_collective(sqt_handle *h, int p, long long n_total, bool split)
+{
+	const int S = h->S, T = h->T, B = h->B;
+	if (split) {
+		CU(cudaEventRecord(h->ev_rho, h->s_main));
+		CU(cudaStreamWaitEvent(h->s_coll, h->ev_rho, 0));
+	}
+	if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_rho_cur, (size_t)h->rho_n * (h->flag_V ? 2 : 1), h->s_coll, h->err, sizeof(h->err)))
+		return SQT_ERR_NCCL;
+	CollectiveArgs ca;
+	ca.rho_cur = h->d_rho_cur; ca.rho0 = h->d_rho0; ca.sumr0 = h->d_sumr0; ca.bufF = h->d_bufF; ca.bufMSDCM = h->d_bufMSDCM;
+	ca.p = p; ca.T = T; ca.B = B; ca.nCS = S;
+	ca.inv_n2 = 1.0 / ((double)n_total * (double)n_total);
+	ca.flag_V = h->flag_V; ca.kvel0 = h->d_kvel0; ca.sumv0 = h->d_sumv0; ca.bufC2 = h->d_bufC2; ca.bufCvcm = h->d_bufCvcm;
+	int rc = sqt_launch_collective(ca, h->s_coll);
+	if (rc) return fail(h, SQT_ERR_CUDA, "collective_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+	h->launches++;
+	CU(cudaEventRecord(h->ev_rhoc, h->s_coll));
+	h->rhoc_pending = true;
 	return SQT_OK;
 }
 
@@ -388,107 +515,110 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	h->kVal = 2. * M_PI / h->L;            // :1632
 	const double invL = 1.0 / h->L;
 	const int p = h->p_file;
+	const bool split = h->s_coll != h->s_main;
+	int rc;
 
 	int varbox = 0;
 	for (int nb = 0; nb < B; ++nb)
 		if (h->count[nb] > 0 && h->h_invL0[nb] != invL) { varbox = 1; break; }
 
-	const int Bc = (h->mc.on || h->vc.on) ? 0 : B; // slots the classic kernel treats as real
-	RingArgs ra;
-	ra.cur = h->d_cur[slot]; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
-	ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = h->cur_pitch; ra.n_local = h->n_local;
-	ra.tile = h->kc.tile; ra.ntiles = h->kc.ntiles; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
-	ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = Bc; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
-	ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
-	ra.varbox = varbox;
-	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-	if (h->prof) {
-		CU(cudaEventCreate(&pe0)); CU(cudaEventCreate(&pe1));
-		CU(cudaEventRecord(pe0, h->s_main));
-	}
-	int rc;
-	if (h->vc.on) {
-		MmaArgs ma;
-		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
-		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local; ma.tile = h->vc.tile;
-		ma.ntiles = h->vc.ntiles; ma.NWSG = h->vc.NWSG; ma.KW = h->vc.KW; ma.total_warps = h->vc.total_warps; ma.dynamic = h->vc.dynamic;
-		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = 0; ma.NT = 0; ma.invL = invL;
-		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
-		rc = sqt_launch_vec(h->vc, ma, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_vec_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-	}
-	if (h->mc.on) {
-		MmaArgs ma;
-		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
-		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local; ma.tile = h->mc.tile;
-		ma.ntiles = h->mc.ntiles; ma.NWSG = h->mc.NWSG; ma.KW = h->mc.KW; ma.total_warps = h->mc.total_warps; ma.dynamic = h->mc.dynamic;
-		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = h->mc.S; ma.NT = h->mc.NT; ma.invL = invL;
-		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
-		rc = sqt_launch_mma(h->mc, ma, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-	}
-	const bool split = h->s_coll != h->s_main;
-	if (h->rmc.on) { // rho(k) and sum_n r on the tensor-core path too: the classic kernel is not launched at all
-		// its reduce rewrites d_rho_cur, which the previous frame's allreduce + collective stage (other stream) still reads
-		if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
+	// ---- stage A: rho(k) of this frame first, so that its allreduce, the F(q,t) update and a caller waiting in
+	// sqt_get_rho are not queued behind the (long) self-term kernel -------------------------------------------------
+	if (h->rmc.on) {
+		// the reduce rewrites d_rho_cur, which the previous frame's allreduce + collective stage (other stream) still reads
+		if (split && h->rhoc_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_rhoc, 0));
+		cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+		if (h->prof) { pe0 = prof_event(h); pe1 = prof_event(h); CU(cudaEventRecord(pe0, h->s_main)); }
 		RhoMmaArgs qa;
-		qa.cur = h->d_cur[slot]; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT; qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
+		qa.cur = h->d_cur[slot]; qa.wt = nullptr; qa.kfac = 0.0; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT;
+		qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
 		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.n_sets = h->rmc.blocks; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
 		rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches += 2;
+		if (h->flag_V) { // kvel_q1 (lmp2sqt.c:1203-1208): the same pass with the velocity component as the particle's weight
+			qa.wt = h->d_cur[slot] + 3 * h->cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + h->rho_n;
+			rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
+			if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel (velocity-weighted) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+			h->launches += 2;
+		}
+		if (h->prof) CU(cudaEventRecord(pe1, h->s_main));
+		if (h->self_kind != SELF_CLASSIC) { rc = stage_collective(h, p, n_total, split); if (rc) return rc; }
+	}
+
+	// ---- stage B: the per-particle terms over the origin ring ---------------------------------------------------------
+	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+	if (h->prof) { pe0 = prof_event(h); pe1 = prof_event(h); CU(cudaEventRecord(pe0, h->s_main)); }
+	MmaArgs ma;
+	if (h->self_kind == SELF_MMA || h->self_kind == SELF_VEC) {
+		const bool mm = h->self_kind == SELF_MMA;
+		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local;
+		ma.tile = mm ? h->mc.tile : h->vc.tile; ma.ntiles = mm ? h->mc.ntiles : h->vc.ntiles; ma.NWSG = mm ? h->mc.NWSG : h->vc.NWSG;
+		ma.KW = mm ? h->mc.KW : h->vc.KW; ma.total_warps = mm ? h->mc.total_warps : h->vc.total_warps; ma.dynamic = mm ? h->mc.dynamic : h->vc.dynamic;
+		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = mm ? h->mc.S : 0; ma.NT = mm ? h->mc.NT : 0; ma.invL = invL;
+		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+		rc = mm ? sqt_launch_mma(h->mc, ma, h->s_main) : sqt_launch_vec(h->vc, ma, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "self_ring_mma_kernel" : "self_ring_vec_kernel", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
-	} else {
+	}
+	const bool classic_launch = h->self_kind == SELF_CLASSIC || !h->rmc.on; // its own slots, or just the six virtual rho(k) slots
+	const int Bc = h->self_kind == SELF_CLASSIC ? B : 0; // slots the classic kernel treats as real
+	if (classic_launch) {
+		RingArgs ra;
+		ra.cur = h->d_cur[slot]; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
+		ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = h->cur_pitch; ra.n_local = h->n_local;
+		ra.tile = h->kc.tile; ra.ntiles = h->kc.ntiles; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
+		ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = Bc; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
+		ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
+		ra.varbox = varbox;
 		rc = sqt_launch_ring(h->kc, ra, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
 	}
-	if (h->prof) { CU(cudaEventRecord(pe1, h->s_main)); h->prof_ev.push_back(pe0); h->prof_ev.push_back(pe1); }
-	CU(cudaEventRecord(h->ev_ring[slot], h->s_main));
-	h->launches++;
+	if (h->prof) CU(cudaEventRecord(pe1, h->s_main));
 
-	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0)); // previous frame's collective stage
-	ReduceArgs rr;
-	rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
-	rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
-	rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.rho_cur = h->d_rho_cur; rr.invL0 = h->d_invL0; rr.invL = invL;
-	if (h->vc.on) {
+	// what follows rewrites per-buffer arrays the previous frame's accumulate stage (other stream) may still read
+	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
+	if (h->d_vring) { // -V -t: rrCvv over the origin-velocity ring (lmp2sqt.c:1397-1401, 1441)
+		VelArgs va;
+		va.vcur = h->d_cur[slot] + 3 * h->cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
+		va.cur_pitch = h->cur_pitch; va.RP = h->ring_np; va.n_local = h->n_local; va.nchunk = h->vel_nchunk; va.chunk = h->vel_chunk;
+		va.p = p; va.T = T; va.B = B;
+		rc = sqt_launch_vel(va, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "vel_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches += 2;
+	}
+	CU(cudaEventRecord(h->ev_ring[slot], h->s_main)); // d_cur[slot] may be overwritten by the copy of the frame after next
+
+	if (h->self_kind == SELF_MMA || h->self_kind == SELF_VEC) {
+		const bool mm = h->self_kind == SELF_MMA;
 		MmaReduceArgs mr;
-		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = 0; mr.n_local = h->n_local; mr.KW = h->vc.KW; mr.NWSG = h->vc.NWSG;
-		mr.S = 0; mr.NT = h->vc.C + 2; mr.SPW = h->vc.SPW;
+		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = mm ? h->mc.SPOUT : 0; mr.n_local = h->n_local;
+		mr.KW = mm ? h->mc.KW : h->vc.KW; mr.NWSG = mm ? h->mc.NWSG : h->vc.NWSG;
+		mr.S = mm ? h->mc.S : 0; mr.NT = mm ? h->mc.NT : h->vc.C + 2; mr.SPW = mm ? h->mc.SPW : h->vc.SPW;
 		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
 		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
-		rc = sqt_launch_vec_reduce(mr, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "vec_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		rc = mm ? sqt_launch_mma_reduce(mr, h->s_main) : sqt_launch_vec_reduce(mr, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "mma_reduce_kernel" : "vec_reduce_kernel", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
 	}
-	if (h->mc.on) {
-		MmaReduceArgs mr;
-		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = h->mc.SPOUT; mr.n_local = h->n_local; mr.KW = h->mc.KW; mr.NWSG = h->mc.NWSG; mr.S = h->mc.S; mr.NT = h->mc.NT; mr.SPW = h->mc.SPW;
-		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
-		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
-		rc = sqt_launch_mma_reduce(mr, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "mma_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-	}
-	if (!h->rmc.on) {
+	if (classic_launch) {
+		ReduceArgs rr;
+		rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
+		rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
+		rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.invL0 = h->d_invL0; rr.invL = invL;
+		// with the tensor-core rho kernel on (-V on the recurrence path) rho(k) is already final: the virtual slots' copy goes to scratch
+		rr.rho_cur = h->rmc.on ? h->d_rho_cur + 2 * h->rho_n : h->d_rho_cur;
 		rc = sqt_launch_reduce(rr, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
+		if (!h->rmc.on || h->self_kind == SELF_CLASSIC) { rc = stage_collective(h, p, n_total, split); if (rc) return rc; }
 	}
 	if (split) {
 		CU(cudaEventRecord(h->ev_red, h->s_main));
 		CU(cudaStreamWaitEvent(h->s_coll, h->ev_red, 0));
 	}
-	if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_rho_cur, 6 * (size_t)S + 3, h->s_coll, h->err, sizeof(h->err)))
-		return SQT_ERR_NCCL;
-	CollectiveArgs ca;
-	ca.rho_cur = h->d_rho_cur; ca.rho0 = h->d_rho0; ca.sumr0 = h->d_sumr0; ca.bufF = h->d_bufF; ca.bufMSDCM = h->d_bufMSDCM;
-	ca.p = p; ca.T = T; ca.B = B; ca.nCS = S;
-	ca.inv_n2 = 1.0 / ((double)n_total * (double)n_total);
-	rc = sqt_launch_collective(ca, h->s_coll);
-	if (rc) return fail(h, SQT_ERR_CUDA, "collective_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-	h->launches++;
 
 	// ---- ring state machine, lmp2sqt.c:1638-1647 -------------------------------------------
 	for (int nb = 0; nb < B; ++nb) {
@@ -497,17 +627,20 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	}
 	// ---- AccumSpacetimeCorr, lmp2sqt.c:376-443 ---------------------------------------------
 	int status = SQT_OK;
+	const size_t ST = (size_t)S * T;
 	for (int nb = 0; nb < B; ++nb) {
 		if (h->count[nb] != T) continue;
 		AccumArgs aa;
-		aa.nb = nb; aa.T = T; aa.nCS = S;
+		aa.nb = nb; aa.T = T; aa.nCS = S; aa.B = B;
 		aa.bufF = h->d_bufF; aa.bufFs = h->d_bufFs; aa.bufMSD = h->d_bufMSD; aa.bufMQD = h->d_bufMQD; aa.bufMSDCM = h->d_bufMSDCM;
 		aa.bufHist = h->d_bufHist; aa.cblk = h->d_cblk;
-		for (int i = 0; i < 7; ++i) aa.av[i] = h->d_avblk + (size_t)i * S * T;
-		for (int i = 0; i < 3; ++i) aa.av1[i] = h->d_avblk + (size_t)7 * S * T + (size_t)i * T;
+		aa.flag_f = h->flag_f; aa.flag_F = h->flag_F; aa.flag_t = h->flag_t; aa.flag_V = h->flag_V;
+		aa.bufC2 = h->d_bufC2; aa.bufCvv = h->d_bufCvv; aa.bufCvcm = h->d_bufCvcm;
+		for (int i = 0; i < 10; ++i) aa.av[i] = h->d_avblk + (size_t)i * ST;
+		for (int i = 0; i < 5; ++i) aa.av1[i] = h->d_avblk + 10 * ST + (size_t)i * T;
 		rc = sqt_launch_pack(aa, h->s_coll);
 		if (rc) return fail(h, SQT_ERR_CUDA, "buffer_pack_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * (size_t)T * S + 2 * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
+		if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * ST + 3 * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
 			return SQT_ERR_NCCL;
 		rc = sqt_launch_accumulate(aa, h->s_coll);
 		if (rc) return fail(h, SQT_ERR_CUDA, "buffer_accumulate_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -533,9 +666,15 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	return status;
 }
 
-static int push_common(sqt_handle *h, const double *src, bool on_device, int n_local, long long n_total, double xlo, double xhi)
+// comp[0..ncomp): host pointers of the frame's arrays (x y z [vx vy vz]), or comp[0] = device SoA when on_device
+static int push_common(sqt_handle *h, const double *const *comp, bool on_device, void *producer_stream, int n_local, long long n_total,
+                       double xlo, double xhi)
 {
-	if (!h || !src || n_local < 1 || n_total < n_local) return h ? fail(h, SQT_ERR_ARG, "push_frame: bad arguments") : SQT_ERR_ARG;
+	if (!h || !comp || !comp[0] || n_local < 1 || n_total < n_local) return h ? fail(h, SQT_ERR_ARG, "push_frame: bad arguments") : SQT_ERR_ARG;
+	if (h->broken) return fail(h, SQT_ERR_STATE, "the handle failed while sizing its arrays for the first frame and cannot take frames");
+	if (!on_device)
+		for (int a = 0; a < h->ncomp; ++a)
+			if (!comp[a]) return fail(h, SQT_ERR_ARG, "push_frame: -V needs the velocity arrays");
 	if (!(xhi > xlo)) return fail(h, SQT_ERR_ARG, "push_frame: box xhi must exceed xlo");
 	if (h->nSkip < h->p.nCSkip) { h->nSkip++; return SQT_OK; } // lmp2sqt.c:1612-1615
 	CU(cudaSetDevice(h->device));
@@ -545,34 +684,44 @@ static int push_common(sqt_handle *h, const double *src, bool on_device, int n_l
 		            h->n_local, h->nPtls, n_local, n_total);
 	int slot;
 	if (on_device) {
-		// engine-owned copy so the producer may overwrite its buffer as soon as later work on
-		// the legacy default stream is ordered after ours (both engine streams are blocking streams)
+		// engine-owned copy, so the producer may refill its buffer.  Ordering against the producer: the legacy default stream
+		// synchronises with the engine's (blocking) streams by itself; any other producer stream is named by the caller
 		slot = h->stage_next; h->stage_next ^= 1;
-		int rc = sqt_launch_soa_copy(h->d_cur[slot], h->cur_pitch, src, n_local, n_local, h->s_main);
+		if (producer_stream) {
+			CU(cudaEventRecord(h->ev_prod, (cudaStream_t)producer_stream));
+			CU(cudaStreamWaitEvent(h->s_main, h->ev_prod, 0));
+		}
+		int rc = sqt_launch_soa_copy(h->d_cur[slot], h->cur_pitch, comp[0], n_local, n_local, h->ncomp, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "soa_copy launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
+		if (producer_stream) {
+			CU(cudaEventRecord(h->ev_prod, h->s_main));
+			CU(cudaStreamWaitEvent((cudaStream_t)producer_stream, h->ev_prod, 0));
+		}
 	} else {
-		const double *stage = src;
-		if (src == h->h_stage[0] && h->stage_cap) slot = 0;
-		else if (src == h->h_stage[1] && h->stage_cap) slot = 1;
+		const double *src[6];
+		for (int a = 0; a < h->ncomp; ++a) src[a] = comp[a];
+		if (comp[0] == h->h_stage[0] && h->stage_cap) slot = 0;
+		else if (comp[0] == h->h_stage[1] && h->stage_cap) slot = 1;
 		else {
 			cudaPointerAttributes pa;
-			bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+			bool pinned = cudaPointerGetAttributes(&pa, comp[0]) == cudaSuccess && pa.type == cudaMemoryTypeHost;
 			cudaGetLastError(); // pageable memory makes the query fail on some drivers: not an error here
 			if (pinned) { slot = h->stage_next; h->stage_next ^= 1; }
 			else { // pageable host memory: one extra host copy into pinned staging
 				double *st = sqt_stage_acquire(h, n_local);
 				if (!st) return SQT_ERR_CUDA;
-				memcpy(st, src, sizeof(double) * 3 * (size_t)n_local);
-				stage = st;
+				for (int a = 0; a < h->ncomp; ++a) {
+					memcpy(st + (size_t)a * n_local, comp[a], sizeof(double) * (size_t)n_local);
+					src[a] = st + (size_t)a * n_local;
+				}
 				slot = (st == h->h_stage[0]) ? 0 : 1;
 			}
 		}
-		// cur[slot] is free once the ring kernel that read it two frames ago has run
+		// cur[slot] is free once the kernels that read it two frames ago have run
 		CU(cudaStreamWaitEvent(h->s_copy, h->ev_ring[slot], 0));
-		for (int a = 0; a < 3; ++a)
-			CU(cudaMemcpyAsync(h->d_cur[slot] + a * h->cur_pitch, stage + (size_t)a * n_local, sizeof(double) * n_local,
-			                   cudaMemcpyHostToDevice, h->s_copy));
+		for (int a = 0; a < h->ncomp; ++a)
+			CU(cudaMemcpyAsync(h->d_cur[slot] + a * h->cur_pitch, src[a], sizeof(double) * n_local, cudaMemcpyHostToDevice, h->s_copy));
 		CU(cudaEventRecord(h->ev_copy[slot], h->s_copy));
 		h->copy_pending[slot] = true;
 		CU(cudaStreamWaitEvent(h->s_main, h->ev_copy[slot], 0));
@@ -582,13 +731,34 @@ static int push_common(sqt_handle *h, const double *src, bool on_device, int n_l
 
 extern "C" int sqt_push_frame(sqt_handle *h, const double *soa, int n_local, long long n_total, double xlo, double xhi)
 {
-	return push_common(h, soa, false, n_local, n_total, xlo, xhi);
+	if (!h || !soa || n_local < 1) return h ? fail(h, SQT_ERR_ARG, "push_frame: bad arguments") : SQT_ERR_ARG;
+	const double *comp[6];
+	for (int a = 0; a < 6; ++a) comp[a] = a < h->ncomp ? soa + (size_t)a * n_local : nullptr;
+	return push_common(h, comp, false, nullptr, n_local, n_total, xlo, xhi);
+}
+
+extern "C" int sqt_push_frame_xyz(sqt_handle *h, const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                                  const double *vz, int n_local, long long n_total, double xlo, double xhi)
+{
+	const double *comp[6] = { x, y, z, vx, vy, vz };
+	if (h && (!y || !z)) return fail(h, SQT_ERR_ARG, "push_frame_xyz: null coordinate array");
+	return push_common(h, comp, false, nullptr, n_local, n_total, xlo, xhi);
 }
 
 extern "C" int sqt_push_frame_device(sqt_handle *h, const double *d_soa, int n_local, long long n_total, double xlo, double xhi)
 {
-	return push_common(h, d_soa, true, n_local, n_total, xlo, xhi);
+	const double *comp[6] = { d_soa, nullptr, nullptr, nullptr, nullptr, nullptr };
+	return push_common(h, comp, true, nullptr, n_local, n_total, xlo, xhi);
 }
+
+extern "C" int sqt_push_frame_device_ex(sqt_handle *h, const double *d_soa, int n_local, long long n_total, double xlo, double xhi,
+                                        void *producer_stream)
+{
+	const double *comp[6] = { d_soa, nullptr, nullptr, nullptr, nullptr, nullptr };
+	return push_common(h, comp, true, producer_stream, n_local, n_total, xlo, xhi);
+}
+
+cudaStream_t sqt_internal_copy_stream(sqt_handle *h) { return h->s_copy; }
 
 extern "C" int sqt_sync(sqt_handle *h)
 {
@@ -606,10 +776,11 @@ static int copy_results(sqt_handle *h, const double *d_blk, sqt_results *out, in
 	int rc = sqt_sync(h);
 	if (rc) return rc;
 	const size_t ST = (size_t)h->S * h->T, T = h->T;
-	double *a2[7] = { out->avF_qq2, out->StdDevF_qq2, out->avF_s_qq2, out->StdDevF_s_qq2, out->avF_d_qq2, out->StdDevF_d_qq2, out->avDrTable };
-	double *a1[3] = { out->rrMSDAv, out->rrMQDAv, out->rrMSDCMAv };
-	for (int i = 0; i < 7; ++i) CU(cudaMemcpy(a2[i], d_blk + i * ST, sizeof(double) * ST, cudaMemcpyDeviceToHost));
-	for (int i = 0; i < 3; ++i) CU(cudaMemcpy(a1[i], d_blk + 7 * ST + i * T, sizeof(double) * T, cudaMemcpyDeviceToHost));
+	double *a2[10] = { out->avF_qq2, out->StdDevF_qq2, out->avF_s_qq2, out->StdDevF_s_qq2, out->avF_d_qq2, out->StdDevF_d_qq2, out->avDrTable,
+	                   out->avC2_v_rho, out->avC2_rho_v, out->avC2_v_v };
+	double *a1[5] = { out->rrMSDAv, out->rrMQDAv, out->rrMSDCMAv, out->rrCvvAv, out->rrCvcmvcmAv };
+	for (int i = 0; i < 10; ++i) if (a2[i]) CU(cudaMemcpy(a2[i], d_blk + i * ST, sizeof(double) * ST, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 5; ++i) if (a1[i]) CU(cudaMemcpy(a1[i], d_blk + 10 * ST + i * T, sizeof(double) * T, cudaMemcpyDeviceToHost));
 	out->countCorrAv = count;
 	out->limitCorrAv = limit;
 	out->nPtls = h->nPtls;
@@ -652,19 +823,43 @@ extern "C" int sqt_number_call_print(const sqt_handle *h) { return h ? h->n_prin
 extern "C" long long sqt_kernel_launches(const sqt_handle *h) { return h ? h->launches : 0; }
 extern "C" const char *sqt_kernel_config(const sqt_handle *h) { return h ? h->cfg : ""; }
 
+// d_rho_cur (+ offset) of the last processed frame to the host, waiting only for that frame's rho stage: the copy goes
+// through a non-blocking stream of its own (a plain cudaMemcpy would synchronise with the engine's blocking streams and
+// hence wait for the self-term kernel)
+static int read_rho_block(sqt_handle *h, double *out, int offset)
+{
+	CU(cudaSetDevice(h->device));
+	if (h->rhoc_pending) CU(cudaStreamWaitEvent(h->s_aux, h->ev_rhoc, 0));
+	CU(cudaMemcpyAsync(out, h->d_rho_cur + offset, sizeof(double) * 6 * h->S, cudaMemcpyDeviceToHost, h->s_aux));
+	CU(cudaStreamSynchronize(h->s_aux));
+	return SQT_OK;
+}
+
 extern "C" int sqt_get_rho(sqt_handle *h, double *out)
 {
 	if (!h || !out) return SQT_ERR_ARG;
-	int rc = sqt_sync(h);
-	if (rc) return rc;
-	CU(cudaMemcpy(out, h->d_rho_cur, sizeof(double) * 6 * h->S, cudaMemcpyDeviceToHost));
-	return SQT_OK;
+	return read_rho_block(h, out, 0);
+}
+
+extern "C" int sqt_get_kvel(sqt_handle *h, double *out)
+{
+	if (!h || !out) return SQT_ERR_ARG;
+	if (!h->flag_V) return fail(h, SQT_ERR_STATE, "sqt_get_kvel: the handle was created without flag_V");
+	return read_rho_block(h, out, h->rho_n);
 }
 
 extern "C" int sqt_profile_enable(sqt_handle *h, int enable)
 {
 	if (!h) return SQT_ERR_ARG;
 	h->prof = enable != 0;
+	if (h->prof) { // four events per frame; prepared here so that frames pushed while profiling create nothing
+		CU(cudaSetDevice(h->device));
+		while (h->prof_pool.size() < 4 * 4096) {
+			cudaEvent_t e = nullptr;
+			CU(cudaEventCreate(&e));
+			h->prof_pool.push_back(e);
+		}
+	}
 	return SQT_OK;
 }
 
@@ -674,15 +869,16 @@ extern "C" int sqt_profile_read(sqt_handle *h, long long *n_launches, double *ms
 	int rc = sqt_sync(h);
 	if (rc) return rc;
 	double tot = 0;
-	for (size_t i = 0; i + 1 < h->prof_ev.size(); i += 2) {
+	for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
 		float ms = 0;
-		CU(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+		CU(cudaEventElapsedTime(&ms, h->prof_pool[i], h->prof_pool[i + 1]));
 		tot += ms;
 	}
-	if (n_launches) *n_launches = (long long)(h->prof_ev.size() / 2);
+	// one pair around the rho(k) kernels (when they are separate launches) and one around the self-term kernel per frame
+	const size_t per_frame = h->rmc.on ? 4 : 2;
+	if (n_launches) *n_launches = (long long)(h->prof_used / per_frame);
 	if (ms_total) *ms_total = tot;
-	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-	h->prof_ev.clear();
+	h->prof_used = 0;
 	return SQT_OK;
 }
 

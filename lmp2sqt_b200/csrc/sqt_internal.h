@@ -87,14 +87,19 @@ struct VecChoice {
 	int C, SPW, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // C = nCSpatial rounded up to 4
 	size_t smem;
 };
-int sqt_pick_vec(int nCS, int B, int n_local, int n_sm, VecChoice *vc);
+// nChain = recurrence steps per (particle, origin, axis): nCSpatial, or 1 when F_s is not wanted (-f / -t without -F): the
+// kernel then only serves MSD, MQD and the van Hove histogram, whatever nCSpatial is
+int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, VecChoice *vc);
 int sqt_launch_vec(const VecChoice &vc, const MmaArgs &a, cudaStream_t st);
 int sqt_launch_vec_reduce(const MmaReduceArgs &a, cudaStream_t st);
 
 struct RhoMmaArgs {
 	const double *cur;        // current frame, SoA [3][cur_pitch]
+	const double *wt;         // nullptr: rho(k).  Else per-particle weights, SoA [3][cur_pitch] (the velocities): the pass then
+	                          // yields the current density kvel_q1 (lmp2sqt.c:1203-1208) = m kVal sum_n v_a (-sin, +cos)(m k0 x_a)
+	double kfac;              // kVal of the current frame (weighted pass only)
 	double *partial;          // per-block fragments [block][axis][cos|sin][NT][32 lanes][2]
-	double *rho_cur;          // [3][nCS][Re,Im] then sum_n r_a [3]
+	double *rho_cur;          // [3][nCS][Re,Im] then sum_n r_a [3]   (weighted pass: kvel, then sum_n v_a)
 	long long cur_pitch;
 	double *extra;            // SPOUT: per-block sum_n r_a [block][3]
 	int n_local, total_warps, n_sets, nCS, S, NT, spout; // n_sets = blocks = partial sets
@@ -125,13 +130,19 @@ struct ReduceArgs {
 int sqt_launch_reduce(const ReduceArgs &a, cudaStream_t st);
 
 struct CollectiveArgs {
-	const double *rho_cur;    // reduced over shards
+	const double *rho_cur;    // reduced over shards: rho [6 nCS], sum r [3]; with -V then kvel [6 nCS], sum v [3]
 	double *rho0;             // [B][6 nCS]
 	double *sumr0;            // [B][3]
 	double *bufF;             // [B][T][nCS]
 	double *bufMSDCM;         // [B][T]   (never zeroed: cumulative, lmp2sqt.c:1450)
 	int p, T, B, nCS;
 	double inv_n2;            // 1 / N^2
+	// -V (flag_velocity): current correlators, lmp2sqt.c:1542-1555, 1452-1457
+	int flag_V;
+	double *kvel0;            // [B][6 nCS]
+	double *sumv0;            // [B][3]
+	double *bufC2;            // [3][B][T][nCS]: C2_v_rho, C2_rho_v, C2_v_v
+	double *bufCvcm;          // [B][T]
 };
 int sqt_launch_collective(const CollectiveArgs &a, cudaStream_t st);
 
@@ -140,14 +151,35 @@ struct AccumArgs {
 	int nb, T, nCS;
 	const double *bufF, *bufFs, *bufMSD, *bufMQD, *bufMSDCM;
 	const int *bufHist;
-	double *cblk;             // packed block [Fs T*nCS | MSD T | MQD T | hist T*nCS]  (allreduced between pack and accumulate)
-	double *av[7];            // avF sdF avFs sdFs avFd sdFd avHist   [nCS][T]
-	double *av1[3];           // msd mqd msdcm [T]
+	double *cblk;             // packed block [Fs T*nCS | MSD T | MQD T | hist T*nCS | Cvv T]  (allreduced between pack and accumulate)
+	double *av[10];           // avF sdF avFs sdFs avFd sdFd avHist  avC2_v_rho avC2_rho_v avC2_v_v   [nCS][T]
+	double *av1[5];           // msd mqd msdcm  cvv cvcmvcm [T]
+	// what AccumSpacetimeCorr adds depends on the getopt flags (lmp2sqt.c:381-432): F under -f, F_s / F_d under -F,
+	// DrTable under -f and -t (EvalTwoTimeEach sits inside `if (flag_t)`, :1370), MSD / MQD / MSDCM under -t
+	int flag_f, flag_F, flag_t, flag_V;
+	const double *bufC2, *bufCvv, *bufCvcm; // -V: [3][B][T][nCS], [B][T], [B][T]
+	int B;
 };
 int sqt_launch_pack(const AccumArgs &a, cudaStream_t st);
 int sqt_launch_accumulate(const AccumArgs &a, cudaStream_t st);
 
-int sqt_launch_soa_copy(double *dst, long long dst_pitch, const double *src, long long src_pitch, int n, cudaStream_t st);
+int sqt_launch_soa_copy(double *dst, long long dst_pitch, const double *src, long long src_pitch, int n, int ncomp, cudaStream_t st);
+
+// ---- sqt_vel.cu: velocity autocorrelation over the origin ring (-V: rrCvv, lmp2sqt.c:1397-1401, 1441) ----------------
+struct VelArgs {
+	const double *vcur;       // current velocities, SoA [3][cur_pitch]
+	double *vring;            // origin velocities [slot][3][RP]
+	double *partial;          // [B][nchunk]
+	double *bufCvv;           // [B][T]
+	long long cur_pitch, RP;
+	int n_local, nchunk, chunk;
+	int p, T, B;
+};
+int sqt_launch_vel(const VelArgs &a, cudaStream_t st);   // vel_ring_kernel + vel_reduce_kernel
+
+// ---- sqt_api.cu internals used by sqt_multi.cu -------------------------------------------------
+struct sqt_handle;
+cudaStream_t sqt_internal_copy_stream(sqt_handle *h); // the stream the handle's H2D copies are issued on
 
 // ---- sqt_comm.cpp -------------------------------------------------------------------------
 struct SqtComm;

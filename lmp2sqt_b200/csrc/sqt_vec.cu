@@ -162,9 +162,9 @@ __global__ void vec_reduce_kernel(const MmaReduceArgs a)
 				const double *p = a.partial + ((long long)(wsg * a.KW) * SPW + s) * W + m;
 				const long long stride = (long long)SPW * W;
 				const double v = strided_sum(p, stride, 0, a.KW, 1);
-				if (m < a.nCS) a.bufFs[((long long)slot * a.T + tau) * a.nCS + m] = v;
-				else if (m == W - 2) a.bufMSD[slot * a.T + tau] = v;
+				if (m == W - 2) a.bufMSD[slot * a.T + tau] = v;
 				else if (m == W - 1) a.bufMQD[slot * a.T + tau] = v;
+				else if (m < a.nCS) a.bufFs[((long long)slot * a.T + tau) * a.nCS + m] = v; // (fewer chains than nCSpatial: F_s not wanted)
 			}
 			if (threadIdx.x == 0 && tau == 0) a.invL0[slot] = a.invL;
 			for (int bin = threadIdx.x; bin < a.nCS; bin += blockDim.x)
@@ -193,12 +193,12 @@ static int vec_env_int(const char *name, int dflt)
 	return (s && *s) ? atoi(s) : dflt;
 }
 
-int sqt_pick_vec(int nCS, int B, int n_local, int n_sm, VecChoice *vc)
+int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, VecChoice *vc)
 {
 	vc->on = 0;
 	const int want = vec_env_int("SQT_VEC", -1);
-	if (want == 0 || B < 1 || nCS < 1 || nCS > 32) return 0;
-	const int C = (nCS + 3) / 4 * 4;
+	if (want == 0 || B < 1 || nCS < 1 || nChain < 1 || nChain > 32) return 0;
+	const int C = (nChain + 3) / 4 * 4;
 	const int SPW = C <= 12 ? 2 : 1; // 2 C SPW registers of running sums per lane
 	const int W = 4;
 	const size_t sm = sizeof(long long) * (nCS + 2) + sizeof(int) * (size_t)nCS * W * SPW;

@@ -22,8 +22,15 @@ import numpy as np
 from . import _lib
 from ._lib import SQT_FLUSH, SqtDeck, SqtParams, SqtResults
 
-NAMES2D = ["avF_qq2", "StdDevF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "avF_d_qq2", "StdDevF_d_qq2", "avDrTable"]
-NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv"]
+NAMES2D = ["avF_qq2", "StdDevF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "avF_d_qq2", "StdDevF_d_qq2", "avDrTable",
+           "avC2_v_rho", "avC2_rho_v", "avC2_v_v"]          # the last three: -V only (zero otherwise)
+NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv", "rrCvvAv", "rrCvcmvcmAv"]
+
+
+def _flag_ints(flags: str):
+    """getopt flags of the reference (lmp2sqt.c:152-191): -F implies -f."""
+    f_F = "F" in flags
+    return int(f_F or "f" in flags), int(f_F), int("t" in flags), int("V" in flags)
 
 
 class SqtError(RuntimeError):
@@ -88,17 +95,14 @@ class Results:
 
     def normalise(self, deck: Deck, flags: str = "Ft") -> None:
         """prePrintProcess (lmp2sqt.c:576-675), in place."""
-        f_F = "F" in flags
         dk = deck.to_c()
-        _lib.host_lib().sqt_host_normalise(C.byref(self.c), C.byref(dk), int(f_F or "f" in flags), int(f_F), int("t" in flags))
+        _lib.host_lib().sqt_host_normalise_v(C.byref(self.c), C.byref(dk), *_flag_ints(flags))
 
     def print_process(self, outdir: str, deck: Deck, flags: str = "Ft", date: str | None = None) -> None:
         """PrintProcess (lmp2sqt.c:338-367): normalise in place and write the reference's files into ``outdir``."""
-        f_F = "F" in flags
         dk = deck.to_c()
-        rc = _lib.host_lib().sqt_host_print_process(os.fsencode(outdir), C.byref(self.c), C.byref(dk),
-                                                    int(f_F or "f" in flags), int(f_F), int("t" in flags),
-                                                    date.encode() if date else None)
+        rc = _lib.host_lib().sqt_host_print_process_v(os.fsencode(outdir), C.byref(self.c), C.byref(dk), *_flag_ints(flags),
+                                                      date.encode() if date else None)
         if rc:
             raise OSError("sqt_host_print_process failed in %s" % outdir)
 
@@ -110,9 +114,10 @@ class SpacetimeCorr:
         self.lib = _lib.engine_lib()
         self.deck = deck
         self.flags = flags
-        f_F = "F" in flags
+        ff, fF, ft, fV = _flag_ints(flags)
         p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
-                      deck.nCTime, deck.nCSkip, int(f_F or "f" in flags), int(f_F), int("t" in flags), device)
+                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, 0, fV)
+        self.ncomp = 6 if fV else 3
         h = C.c_void_p()
         rc = self.lib.sqt_create(C.byref(p), C.byref(h))
         if rc:
@@ -149,18 +154,22 @@ class SpacetimeCorr:
     begin_file = InitSpacetimeCorr
 
     def stage(self, n_local: int) -> np.ndarray:
-        """Pinned SoA staging for the next frame as a (3, n) float64 view."""
+        """Pinned SoA staging for the next frame as a (3, n) float64 view ((6, n) with -V: x y z vx vy vz)."""
         p = self.lib.sqt_stage_acquire(self.h, int(n_local))
         if not p:
             raise SqtError("sqt_stage_acquire: " + self.lib.sqt_last_error(self.h).decode())
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(3, n_local))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.ncomp, n_local))
 
-    def EvalSpacetimeCorr(self, xyz: np.ndarray, xlo: float, xhi: float, n_total: int | None = None) -> int:
-        """One frame.  ``xyz`` is (n, 3) atoms in dump order (this rank's shard).  Returns SQT_FLUSH (1)
-        when the reference would have called PrintProcess inside AccumSpacetimeCorr."""
+    def EvalSpacetimeCorr(self, xyz: np.ndarray, xlo: float, xhi: float, n_total: int | None = None, vel: np.ndarray | None = None) -> int:
+        """One frame.  ``xyz`` is (n, 3) atoms in dump order (this rank's shard); ``vel`` likewise with -V.  Returns
+        SQT_FLUSH (1) when the reference would have called PrintProcess inside AccumSpacetimeCorr."""
         n = xyz.shape[0]
         st = self.stage(n)
-        st[:] = np.asarray(xyz, dtype=np.float64).T
+        st[:3] = np.asarray(xyz, dtype=np.float64).T
+        if self.ncomp == 6:
+            if vel is None:
+                raise SqtError("-V needs velocities")
+            st[3:] = np.asarray(vel, dtype=np.float64).T
         return self.push_staged(st, n, n_total if n_total is not None else n, xlo, xhi)
 
     push_frame = EvalSpacetimeCorr
@@ -209,6 +218,11 @@ class SpacetimeCorr:
         self._check(self.lib.sqt_get_rho(self.h, out.ctypes.data), "sqt_get_rho")
         return out
 
+    def kvel(self) -> np.ndarray:
+        out = np.zeros((3, self.S, 2))
+        self._check(self.lib.sqt_get_kvel(self.h, out.ctypes.data), "sqt_get_kvel")
+        return out
+
     @property
     def kernel_launches(self) -> int:
         return self.lib.sqt_kernel_launches(self.h)
@@ -237,6 +251,87 @@ class SpacetimeCorr:
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(unique_id, _lib.SQT_COMM_ID_BYTES)
         self._check(self.lib.sqt_comm_init(self.h, buf, rank, nranks), "sqt_comm_init")
+
+
+class MultiSpacetimeCorr:
+    """G GPUs behind one caller thread (include/sqt.h, sqt_multi_*): one pinned frame, fan-out by particle chunk."""
+
+    def __init__(self, deck: Deck, flags: str = "Ft", n_gpus: int = 2, device: int = 0):
+        self.lib = _lib.engine_lib()
+        self.deck, self.flags = deck, flags
+        ff, fF, ft, fV = _flag_ints(flags)
+        p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
+                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, n_gpus, fV)
+        self.ncomp = 6 if fV else 3
+        h = C.c_void_p()
+        rc = self.lib.sqt_multi_create(C.byref(p), C.byref(h))
+        if rc:
+            raise SqtError("sqt_multi_create failed (%d): %s" % (rc, self.lib.sqt_multi_last_error(None).decode()))
+        self.h = h
+        self.S, self.T = deck.nCSpatial, deck.nCTime
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sqt_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> int:
+        if rc < 0:
+            raise SqtError("%s failed (%d): %s" % (what, rc, self.lib.sqt_multi_last_error(self.h).decode()))
+        return rc
+
+    def set_limit(self, v: int):
+        self._check(self.lib.sqt_multi_set_limit(self.h, int(v)), "sqt_multi_set_limit")
+
+    def InitSpacetimeCorr(self):
+        self._check(self.lib.sqt_multi_begin_file(self.h), "sqt_multi_begin_file")
+
+    def EvalSpacetimeCorr(self, xyz, xlo, xhi, n_total=None, vel=None) -> int:
+        n = xyz.shape[0]
+        p = self.lib.sqt_multi_stage_acquire(self.h, n)
+        if not p:
+            raise SqtError("sqt_multi_stage_acquire: " + self.lib.sqt_multi_last_error(self.h).decode())
+        st = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.ncomp, n))
+        st[:3] = np.asarray(xyz, dtype=np.float64).T
+        if self.ncomp == 6:
+            st[3:] = np.asarray(vel, dtype=np.float64).T
+        return self._check(self.lib.sqt_multi_push_frame(self.h, st.ctypes.data, n, float(xlo), float(xhi)), "sqt_multi_push_frame")
+
+    def fetch(self) -> Results:
+        r = Results(self.S, self.T)
+        self._check(self.lib.sqt_multi_fetch_results(self.h, C.byref(r.c)), "sqt_multi_fetch_results")
+        return r
+
+    def finish(self) -> Results | None:
+        r = Results(self.S, self.T)
+        rc = self._check(self.lib.sqt_multi_finish(self.h, C.byref(r.c)), "sqt_multi_finish")
+        return r if rc == 1 else None
+
+    @property
+    def n_gpus(self) -> int:
+        return self.lib.sqt_multi_n_gpus(self.h)
+
+    @property
+    def kernel_config(self) -> str:
+        return self.lib.sqt_kernel_config(self.lib.sqt_multi_handle(self.h, 0)).decode()
+
+    @property
+    def kernel_launches(self) -> int:
+        return self.lib.sqt_multi_kernel_launches(self.h)
+
+    @property
+    def countCorrAv(self) -> int:
+        return self.lib.sqt_count_corr_av(self.lib.sqt_multi_handle(self.h, 0))
+
+    @property
+    def number_call_print(self) -> int:
+        return self.lib.sqt_number_call_print(self.lib.sqt_multi_handle(self.h, 0))
 
 
 def comm_unique_id() -> bytes:
@@ -308,9 +403,10 @@ def shard_bounds(n_total: int, rank: int, nranks: int) -> tuple[int, int]:
 
 
 def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank: int = 0, nranks: int = 1,
-                     unique_id: bytes | None = None, on_flush=None):
+                     unique_id: bytes | None = None, on_flush=None, n_gpus: int = 0):
     """Drive the engine over a list of trajectories (= input files) exactly like the reference's main
-    (lmp2sqt.c:200-333), including its limitCorrAv bookkeeping.  Returns (printed Results | None, engine)."""
+    (lmp2sqt.c:200-333), including its limitCorrAv bookkeeping.  Returns (printed Results | None, engine).
+    ``n_gpus`` > 0 uses the in-process multi-GPU fan-out (sqt_multi_*) instead of one handle."""
     B = max(1, min(deck.nCBuffer, deck.nCTime))
     limit = deck.limitCorrAv
     use = []
@@ -320,18 +416,23 @@ def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank
         use.append(ok)
         if ok:
             limit += (n_snap - deck.nCTime) // (deck.nCTime // B)                    # lmp2sqt.c:244
-    eng = SpacetimeCorr(deck, flags, device)
-    if nranks > 1:
-        eng.comm_init(unique_id, rank, nranks)
+    if n_gpus > 0:
+        eng = MultiSpacetimeCorr(deck, flags, n_gpus, device)
+    else:
+        eng = SpacetimeCorr(deck, flags, device)
+        if nranks > 1:
+            eng.comm_init(unique_id, rank, nranks)
     eng.set_limit(limit)
     printed = None
+    with_v = "V" in flags
     for t, u in zip(trajs, use):
         if not u:
             continue
         eng.InitSpacetimeCorr()
         lo, hi = shard_bounds(t.n_atoms, rank, nranks)
         for f in range(t.n_frames):
-            rc = eng.EvalSpacetimeCorr(t.positions[f, lo:hi], t.box[f, 0, 0], t.box[f, 0, 1], n_total=t.n_atoms)
+            rc = eng.EvalSpacetimeCorr(t.positions[f, lo:hi], t.box[f, 0, 0], t.box[f, 0, 1], n_total=t.n_atoms,
+                                       vel=t.velocities[f, lo:hi] if with_v else None)
             if rc == SQT_FLUSH:
                 printed = eng.fetch()
                 if on_flush:

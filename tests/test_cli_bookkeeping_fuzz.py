@@ -52,4 +52,4 @@ def test_file_acceptance_and_deck_rewrite_match_reference(tmp_path, seed):
     usable = "Check your input options" not in r.stdout
     assert ("Check your input options" not in o.stdout) == usable
     if usable:
-        assert "sqt_create failed" in o.stderr             # got as far as the engine, which needs a GPU
+        assert "sqt_multi_create failed" in o.stderr             # got as far as the engine, which needs a GPU
