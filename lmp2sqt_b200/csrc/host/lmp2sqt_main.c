@@ -73,7 +73,7 @@ int main(int argc, char **argv)
 			snprintf(inputFilename, sizeof(inputFilename), "%s", optarg);
 			printf("intput filename : %s\n", inputFilename);
 			break;
-		case 'V': puts("flag_velocity on :  velocity correlation "); flag_V = true; break; /* lmp2sqt.c:171-174 */
+		case 'V': puts("flag_velocity on : velocity correlation on"); flag_V = true; break; /* lmp2sqt.c:171-173 */
 		case 'g': n_gpus = atoi(optarg); break;
 		case 's': case 'M':
 			fprintf(stderr, "option -%c (stress / magnet correlators) is outside the B200 hot path; use the reference build for it\n", opt);

@@ -47,6 +47,11 @@ CASES = {
     # nCSpatial in the range the tensor-core kernels serve (>= 64); 128 = the second column layout, config 4's nCSpatial
     "g6_nCS70": dict(traj=[dict(n_cells=3, n_atoms=100, n_frames=36, seed=7, box_jitter=0.005)], S=70, T=8, B=8, skip=None, limit=14825, flags="Ft"),
     "g7_nCS128": dict(traj=[dict(n_cells=3, n_frames=30, seed=8)], S=128, T=6, B=3, skip=None, limit=14825, flags="Ft"),
+    # flag combinations without -t / without -F: the van Hove block is all zero without -t (EvalTwoTimeEach as a whole is
+    # `if (flag_t)`, lmp2sqt.c:1370), no Dt file; -t alone writes only the Dt file; -f -t at a tensor-core nCSpatial
+    "g8_F_only": dict(traj=[dict(n_cells=2, n_frames=36, seed=10)], S=6, T=8, B=4, skip=None, limit=14825, flags="F"),
+    "g9_t_only": dict(traj=[dict(n_cells=2, n_frames=36, seed=11)], S=6, T=8, B=4, skip=None, limit=14825, flags="t"),
+    "g10_ft_nCS70": dict(traj=[dict(n_cells=2, n_frames=30, seed=12)], S=70, T=6, B=6, skip=None, limit=14825, flags="ft"),
 }
 # SURVEY.md section 8f.4 (next row, oracle first): -V, dumps with vx vy vz.  Kept apart from CASES: the product's host
 # code and engine do not implement -V yet, only oracle/sqt_oracle.c does; tests/test_oracle.py pins it on this case.

@@ -63,3 +63,44 @@ def test_two_gpu_shards_match_single_gpu_and_oracle(tmp_path, S, T, B):
     for k in ("avF_qq2", "avF_s_qq2", "rrMSDAv", "rrMQDAv"):
         np.testing.assert_allclose(r0[k], s[k], rtol=1e-10, atol=1e-9)
     assert np.array_equal(r0["avDrTable"], s["avDrTable"])
+
+
+# ---- G GPUs behind one caller thread (include/sqt.h sqt_multi_*, CLI -g N): SURVEY.md section 8e frame fan-out ------------
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("S,T,B,flags", [(6, 8, 4, "Ft"), (100, 6, 6, "Ft"), (30, 6, 6, "FtV"), (43, 6, 6, "Ft")])
+def test_in_process_fanout_matches_oracle_and_single_gpu(S, T, B, flags):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    from lmp2sqt_b200 import Deck, run_trajectories, synth
+    from parity import check_raw_sums
+    traj = synth.make_trajectory(n_cells=3, n_atoms=101, n_frames=40, seed=78, box_jitter=0.005)
+    deck = Deck(limitCorrAv=10**6, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res, eng = run_trajectories([traj], deck, flags, n_gpus=2)
+    assert eng.n_gpus == 2
+    got = res.to_dict()
+    _, raw, _ = pyoracle.run_port(traj, S, T, B, limitCorrAv=10**6, flags=flags, finish=False)
+    check_raw_sums(got, raw, traj.n_atoms, label="fan-out x2 ")
+    if "V" in flags:
+        for k in ("avC2_v_rho", "avC2_rho_v", "avC2_v_v", "rrCvvAv", "rrCvcmvcmAv"):
+            np.testing.assert_allclose(got[k], raw[k], rtol=1e-6, atol=1e-9 * np.abs(raw[k]).max(), err_msg=k)
+    single, e1 = run_trajectories([traj], deck, flags)
+    s = single.to_dict()
+    assert np.array_equal(got["avDrTable"], s["avDrTable"])
+    for k in ("avF_qq2", "avF_s_qq2", "rrMSDAv", "rrMQDAv"):
+        np.testing.assert_allclose(got[k], s[k], rtol=1e-10, atol=1e-9)
+    eng.close(); e1.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name", ["g1_midrun_print", "g3_two_files_skip", "g6_nCS70", "g7_nCS128"])
+def test_cli_with_two_gpus_is_still_a_drop_in(name, tmp_path):
+    """`lmp2sqt_b200.out -g 2`: one reader thread, one pinned frame, two chunk copies -- the same files as the reference's."""
+    import shutil
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from golden_utils import case_dir, load_case, unpack_dumps
+    from test_gpu_cli import _run_and_compare
+    c, g = load_case(name), case_dir(name)
+    shutil.copy(os.path.join(g, "in.lmp2sqt"), tmp_path / "in.lmp2sqt")
+    dumps = unpack_dumps(name, str(tmp_path))
+    _run_and_compare(c, g, dumps, tmp_path, ["-g", "2"], expect_in_stderr="2 GPUs, particle-sharded")

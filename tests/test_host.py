@@ -156,22 +156,32 @@ def test_writers_reproduce_reference_files_byte_for_byte(name, tmp_path):
     deck = Deck.read(os.path.join(case_dir(name), "in.lmp2sqt"))
     res.print_process(str(tmp_path), deck, c["flags"], date="GOLD")
     g = case_dir(name)
-    assert filecmp.cmp(tmp_path / "output.binary", os.path.join(g, "output.binary"), shallow=False)
-    assert filecmp.cmp(tmp_path / "output.txt", os.path.join(g, "output.txt"), shallow=False)
+    has_f, has_t = "f" in c["flags"].lower(), "t" in c["flags"]   # which files exist follows the flags (lmp2sqt.c:347-365, 927, 1033)
     assert filecmp.cmp(tmp_path / "output.log", os.path.join(g, "output.log"), shallow=False)
-    assert (tmp_path / "SSF000.info.GOLD").read_text() == open(os.path.join(g, "SSF000.info")).read()
-    got_dt, ref_dt = (tmp_path / "Dt000.info.GOLD").read_text(), open(os.path.join(g, "Dt000.info")).read()
-    if all(ln.split()[2:5] == ["0", "0", "0"] for ln in ref_dt.strip().split("\n")[1:]):
-        assert got_dt == ref_dt                                  # byte for byte when the reference's memory happened to be zero
-    assert dt_rows_without_uninitialised_columns(got_dt) == dt_rows_without_uninitialised_columns(ref_dt)
+    for fn in ("output.binary", "output.txt"):
+        assert (tmp_path / fn).exists() == has_f == os.path.exists(os.path.join(g, fn))
+        if has_f:
+            assert filecmp.cmp(tmp_path / fn, os.path.join(g, fn), shallow=False)
+    assert (tmp_path / "SSF000.info.GOLD").exists() == has_f == os.path.exists(os.path.join(g, "SSF000.info"))
+    if has_f:
+        assert (tmp_path / "SSF000.info.GOLD").read_text() == open(os.path.join(g, "SSF000.info")).read()
+    assert (tmp_path / "Dt000.info.GOLD").exists() == has_t == os.path.exists(os.path.join(g, "Dt000.info"))
+    if has_t:
+        got_dt, ref_dt = (tmp_path / "Dt000.info.GOLD").read_text(), open(os.path.join(g, "Dt000.info")).read()
+        if all(ln.split()[2:5] == ["0", "0", "0"] for ln in ref_dt.strip().split("\n")[1:]):
+            assert got_dt == ref_dt                              # byte for byte when the reference's memory happened to be zero
+        assert dt_rows_without_uninitialised_columns(got_dt) == dt_rows_without_uninitialised_columns(ref_dt)
     # the normalised arrays equal what the reference left in its globals
     got = res.to_dict()
     assert np.array_equal(got["avF_qq2"], printed["avF"]) and np.array_equal(got["rrMSDAv"], printed["rrMSDAv"])
     assert np.array_equal(got["avDrTable"], printed["avDrTable"])
-    # second print in the same directory picks the next free index (lmp2sqt.c:886-902)
+    if not has_t:
+        assert not got["avDrTable"].any()                        # only -t fills the van Hove table (lmp2sqt.c:1370, 1428)
+    # second print in the same directory picks the next free index, probed on the Dt name only (lmp2sqt.c:886-902)
     res2 = _results_from(rp, c["S"], c["T"])
     res2.print_process(str(tmp_path), deck, c["flags"], date="GOLD")
-    assert (tmp_path / "Dt001.info.GOLD").exists() and (tmp_path / "SSF001.info.GOLD").exists()
+    if has_t:
+        assert (tmp_path / "Dt001.info.GOLD").exists() and (tmp_path / "SSF001.info.GOLD").exists() == has_f
 
 
 def test_factor_dr_matches_oracle():

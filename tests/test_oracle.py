@@ -33,6 +33,8 @@ def test_port_reproduces_reference_golden_arrays(name):
 def test_port_reproduces_reference_output_binary(name):
     """output.binary written by the reference CLI (exact fp64) vs the restatement driven like main()."""
     c = load_case(name)
+    if "f" not in c["flags"].lower():
+        pytest.skip("-t alone writes no output.binary (lmp2sqt.c:354)")
     trajs = case_trajectories(name)
     printed, raw, log = pyoracle.run_port(None, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0, limitCorrAv=c["limit"],
                                           files=trajs, flags=c["flags"])
@@ -53,6 +55,8 @@ def test_port_matches_printed_msd_digits(name):
     """MSD / MQD exist in the reference's files only at %8.4g (Dt*.info, lmp2sqt.c:1060): the restatement's
     fp64 values must round to exactly those digits."""
     c = load_case(name)
+    if "t" not in c["flags"]:
+        pytest.skip("no Dt file without -t (lmp2sqt.c:1033)")
     trajs = case_trajectories(name)
     printed, _, _ = pyoracle.run_port(None, c["S"], c["T"], c["B"], nCSkip=c["skip"] or 0, limitCorrAv=c["limit"],
                                       files=trajs, flags=c["flags"])
