@@ -158,38 +158,47 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--atoms-cells", type=int, default=0, help="override the fcc cell count (debugging only; invalidates the line)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+def parity_check(world, rank, local_rank, dist):
+    """Driver-visible evidence that the sharded (NCCL) path computes the same numbers as the reference: before the timed
+    legs a small trajectory at the headline's kernel shape (nCSpatial 171: tensor-core kernels, several particle tiles per
+    rank) runs through a fresh engine on the same ranks, and rank 0's fully reduced raw sums are compared with the oracle
+    restatement run on the host (oracle/: checker only -- nothing timed goes through it).  Tolerances: SURVEY.md section 8a."""
+    import numpy as np
+    from lmp2sqt_b200 import Deck, comm_unique_id, run_trajectories, synth
+    n_cells, S, T, B, frames = 8, 171, 6, 6, 16
+    traj = synth.make_trajectory(n_cells=n_cells, n_frames=frames, seed=20261021)
+    ids = [comm_unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0)
+    deck = Deck(limitCorrAv=10**9, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res, eng = run_trajectories([traj], deck, "Ft", device=local_rank, rank=rank, nranks=world, unique_id=ids[0])
+    got = res.to_dict()
+    kernel = eng.kernel_config.split(" ")[0]
+    eng.close()
+    if rank != 0:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    _, raw, _ = pyoracle.run_port(traj, S, T, B, limitCorrAv=10**9, finish=False)
+    worst = 0.0
+    for g, r in (("avF_qq2", "avF"), ("avF_s_qq2", "avF_s"), ("avF_d_qq2", "avF_d")):
+        y = raw[r]
+        worst = max(worst, float(np.max(np.abs(got[g] - y) / np.maximum(np.abs(y), 1e-3 * np.abs(y[:, :1])))))
+    msd = max(float(np.max(np.abs(got[k][1:] - raw[k][1:]) / np.abs(raw[k][1:]))) for k in ("rrMSDAv", "rrMQDAv"))   # lag 0 is 0 = 0
+    vh = bool(np.array_equal(got["avDrTable"], raw["avDrTable"]))
+    ok = bool(worst <= 1e-6 and msd <= 1e-9 and vh and got["countCorrAv"] == raw["countCorrAv"])
+    return {"n_ranks": world, "n_atoms": traj.n_atoms, "nCSpatial": S, "ring": "%d/%d" % (T, B), "frames": frames, "kernel": kernel,
+            "checker": "oracle/sqt_oracle.c restatement (bit-identical to the unmodified reference, tests/test_oracle.py)",
+            "max_rel_err": worst, "tolerance": 1e-6, "msd_mqd_max_rel_err": msd, "vanhove_exact": vh,
+            "countCorrAv": int(got["countCorrAv"]), "ok": ok}
 
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
 
+def time_workload(wl, K, W, world, rank, local_rank, dist, n_cells_override=0, with_e2e=True, sampler=None):
+    """Fill the ring (untimed), then time K steady-state frames resident in HBM (`value`), the same through host buffers
+    (`e2e`), and the dominant kernels' own launches (for the roofline).  Returns a dict of raw measurements."""
     import numpy as np
     import torch
-    import torch.distributed as dist
-    from lmp2sqt_b200 import Deck, SpacetimeCorr, SynthSource, comm_unique_id, measure_dfma_peak, shard_bounds
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from lmp2sqt_b200 import Deck, SpacetimeCorr, SynthSource, comm_unique_id, shard_bounds
 
     def barrier():
         torch.cuda.synchronize()
@@ -197,30 +206,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    n_cells, S, T, B, desc = WORKLOADS[args.workload]
-    if args.atoms_cells:
-        n_cells = args.atoms_cells
+    n_cells, S, T, B, desc = WORKLOADS[wl]
+    if n_cells_override:
+        n_cells = n_cells_override
         desc += " [DEBUG OVERRIDE: %d cells]" % n_cells
     n_total = 4 * n_cells**3
     lo, hi = shard_bounds(n_total, rank, world)
     n_local = hi - lo
-    K, W = args.steps, args.warmup
     Kvec = 3 * S
-
     deck = Deck(limitCorrAv=10**9, nCBuffer=B, nCSpatial=S, nCTime=T)
     eng = SpacetimeCorr(deck, "Ft", device=local_rank)
     if world > 1:
@@ -230,62 +230,49 @@ def main():
     src = SynthSource(n_cells, lo, n_local, device=local_rank)
     L = src.L
     eng.InitSpacetimeCorr()
-
-    # ---- setup (untimed): fill the origin ring so that every timed frame sees B live origins ----------
     t_fill = time.time()
-    for _ in range(T):
+    for _ in range(T):                       # setup (untimed): every timed frame sees B live origins
         eng.push_device(src.next(), n_local, n_total, 0.0, L)
     eng.sync()
     t_fill = time.time() - t_fill
 
     frame_bytes = 3 * n_local * 8
-    # ---- value leg: frames already resident in HBM -----------------------------------------------------
     pool_n = max(1, min(K, int(12e9 // frame_bytes)))
     pool = [torch.empty(3 * n_local, dtype=torch.float64, device="cuda") for _ in range(pool_n)]
     for _ in range(W):
         eng.push_device(src.next(), n_local, n_total, 0.0, L)
-    frames_in_pool = 0
-
-    def refill_pool(count):
-        for i in range(count):
-            src.next()
-            src.to_device(pool[i].data_ptr())
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    total_ms = 0.0
-    done = 0
+    total_ms, done = 0.0, 0
     launches0 = eng.kernel_launches
     eng.profile(True)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     while done < K:
         chunk = min(pool_n, K - done)
-        refill_pool(chunk)
+        for i in range(chunk):
+            src.next()
+            src.to_device(pool[i].data_ptr())
         barrier()
         eng.timer_start()
         for i in range(chunk):
             eng.push_device(pool[i].data_ptr(), n_local, n_total, 0.0, L)
         ms = eng.timer_stop()
         barrier()
-        total_ms += max_over_ranks(ms)
+        total_ms += reduce_ranks(ms, dist.ReduceOp.MAX if world > 1 else None)
         done += chunk
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     n_ring, ring_ms = eng.profile_read()
     eng.profile(False)
-    launches = eng.kernel_launches - launches0
-    value = n_total * Kvec * K / (total_ms * 1e-3)
-    ms_per_step = total_ms / K
-    ring_ms_avg = max_over_ranks(ring_ms / max(1, n_ring))
+    out = {"wl": wl, "desc": desc, "S": S, "T": T, "B": B, "Kvec": Kvec, "n_total": n_total, "n_local": n_local, "t_fill": t_fill,
+           "launches": eng.kernel_launches - launches0, "total_ms": total_ms, "ms_per_step": total_ms / K,
+           "value": n_total * Kvec * K / (total_ms * 1e-3), "clocks": clocks, "frame_bytes": frame_bytes,
+           "ring_ms_avg": reduce_ranks(ring_ms / max(1, n_ring), dist.ReduceOp.MAX if world > 1 else None), "cfg": eng.kernel_config, "e2e": None}
+    del pool
 
-    # ---- e2e leg: host buffers, H2D inside the timed region, result read back every step ---------------
-    e2e = None
-    if not args.no_e2e:
+    if with_e2e:     # host buffers, H2D inside the timed region, the step's result read back every step
         hp_n = max(1, min(K, int(6e9 // frame_bytes)))
         hpool = [torch.empty(3 * n_local, dtype=torch.float64).pin_memory() for _ in range(hp_n)]
         rho_host = np.zeros((3, S, 2))
-        e2e_ms = 0.0
-        done = 0
+        e2e_ms, done = 0.0, 0
         import ctypes as C
         while done < K:
             chunk = min(hp_n, K - done)
@@ -299,24 +286,32 @@ def main():
                 rc = eng.lib.sqt_push_frame(eng.h, C.c_void_p(hpool[i].data_ptr()), n_local, n_total, 0.0, float(L))
                 if rc < 0:
                     raise RuntimeError(eng.lib.sqt_last_error(eng.h).decode())
-                eng.lib.sqt_get_rho(eng.h, rho_host.ctypes.data)   # D2H read of the step's result (synchronises)
+                eng.lib.sqt_get_rho(eng.h, rho_host.ctypes.data)   # D2H read of the step's result (waits for that step's rho stage)
             ms = eng.timer_stop()
             wall_ms = (time.perf_counter() - t0) * 1e3
             barrier()
-            e2e_ms += max_over_ranks(max(ms, wall_ms))
+            e2e_ms += reduce_ranks(max(ms, wall_ms), dist.ReduceOp.MAX if world > 1 else None)
             done += chunk
-        e2e = {"value": n_total * Kvec * K / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(sum_over_ranks(frame_bytes)), "d2h_bytes_per_step": int(6 * S * 8 * world),
-               "ms_per_step": e2e_ms / K, "api": "sqt_push_frame(pinned host SoA) + sqt_get_rho per step"}
+        out["e2e"] = {"value": n_total * Kvec * K / (e2e_ms * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": int(reduce_ranks(frame_bytes, dist.ReduceOp.SUM if world > 1 else None)),
+                      "d2h_bytes_per_step": int(6 * S * 8 * world), "ms_per_step": e2e_ms / K,
+                      "api": "sqt_push_frame(pinned host SoA) + sqt_get_rho per step; the next step's host-to-device copy runs under this "
+                             "step's self-term kernel (sqt_get_rho waits for the step's rho(k) stage only)"}
+    out["launches"] = int(reduce_ranks(out["launches"], dist.ReduceOp.SUM if world > 1 else None))
+    eng.close()
+    src.close()
+    return out
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------
-    hbm_peak, hbm_src = load_peaks()
-    dfma_tf, dfma_mhz = measure_dfma_peak(local_rank)
+
+def roofline_of(m, dfma_tf, dfma_mhz, hbm_peak, hbm_src, world):
+    """Roofline of the dominant kernels of a measured workload (DESIGN.md sections 4.2, 4.3, 7)."""
+    B, Kvec, n_local = m["B"], m["Kvec"], m["n_local"]
     flops_per_unit = 6 + 3 * B                       # SURVEY.md 8d: rho 2 FMA + 2 ADD, self 1 FMA + 1 ADD per live origin
     units_per_launch = n_local * Kvec
+    ring_ms_avg = m["ring_ms_avg"]
     ach_tf = units_per_launch * flops_per_unit / (ring_ms_avg * 1e-3) / 1e12
     alg_bytes = n_local * 24.0 * (1 + B)             # current positions + B origin positions per particle
-    cfg_now = eng.kernel_config
+    cfg_now = m["cfg"]
     on_mma = cfg_now.startswith("self_ring_mma_kernel")
     family = "self_ring_mma_kernel" if on_mma else ("self_ring_vec_kernel" if cfg_now.startswith("self_ring_vec_kernel") else "self_ring_kernel")
     if on_mma:
@@ -335,8 +330,13 @@ def main():
                                 "HBM is at a few percent (roofline.hbm)",
                 "kernel": family + (" + rho_mma_kernel" if "rho_mma_kernel" in cfg_now else ""),
                 "achieved": ach_tf, "peak": dfma_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / dfma_tf, "traffic": None,
-                "peak_source": "measured live: register-resident DFMA microbenchmark (sqt_measure_dfma_peak), %.0f MHz implied" % dfma_mhz,
+                "frac": ach_tf / dfma_tf, "traffic": None, "traffic_source": None,
+                "peak_source": "measured in THIS run by this repo's own register-resident DFMA microbenchmark (sqt_measure_dfma_peak; %.0f MHz "
+                               "implied); MEASURED_PEAKS.json carries no FP64 peak; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s "
+                               "(frac_of_nominal below)" % dfma_mhz,
+                "frac_of_nominal": ach_tf / 37.2,
+                "achieved_source": "algorithmic flops (SURVEY.md 8d) / CUDA-event time of the rho(k) + self-term kernels' own launches, "
+                                   "measured in this run on their stream",
                 "flops_per_unit": flops_per_unit, "units_per_launch": units_per_launch, "avg_launch_ms": ring_ms_avg,
                 **pipe_note,
                 "hbm": {"achieved": alg_bytes / (ring_ms_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -347,18 +347,90 @@ def main():
         try:
             with open(prof_json) as f:
                 tr = json.load(f)
-            if tr.get("workload") == args.workload and tr.get("n_gpus") == world and tr.get("kernel", "").startswith(family + "<"):
+            if tr.get("workload") == m["wl"] and tr.get("n_gpus") == world and tr.get("kernel", "").startswith(family + "<"):
                 roofline["traffic"] = tr.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the "
+                                              "committed ncu --set full capture " + str(tr.get("source")))
         except Exception:
             pass
+    return roofline
 
-    total_launches = int(sum_over_ranks(launches))
-    cfg = eng.kernel_config
-    eng.close()
-    src.close()
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--atoms-cells", type=int, default=0, help="override the fcc cell count (debugging only; invalidates the line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lmp2sqt_b200 import measure_dfma_peak
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- parity of the (sharded) path against the oracle, before anything is timed ------------------------------------
+    pcheck = None
+    if not args.no_parity_check:
+        pcheck = parity_check(world, rank, local_rank, dist)
+        flag = torch.tensor([1.0 if (rank != 0 or pcheck["ok"]) else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() < 1.0:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "error": "parity_check failed: no number is reported",
+                                  "parity_check": pcheck}), flush=True)
+            raise SystemExit(1)
+
+    K, W = args.steps, args.warmup
+    gpu_index = local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+    sampler = ClockSampler(gpu_index) if rank == 0 else None
+    m = time_workload(args.workload, K, W, world, rank, local_rank, dist, args.atoms_cells, with_e2e=not args.no_e2e, sampler=sampler)
+
+    hbm_peak, hbm_src = load_peaks()
+    dfma_tf, dfma_mhz = measure_dfma_peak(local_rank)
+    roofline = roofline_of(m, dfma_tf, dfma_mhz, hbm_peak, hbm_src, world)
+
+    # ---- the other BASELINE configs (parity-test shapes, not the headline): a few steady-state frames each, one GPU -----
+    others = None
+    if world == 1 and not args.no_other_workloads and not args.atoms_cells:
+        others = {}
+        for wl in sorted(WORKLOADS):
+            if wl == args.workload:
+                continue
+            try:
+                mo = time_workload(wl, 20, 3, 1, 0, local_rank, dist, with_e2e=False)
+                ro = roofline_of(mo, dfma_tf, dfma_mhz, hbm_peak, hbm_src, 1)
+                others[wl] = {"workload": mo["desc"], "ms_per_step": mo["ms_per_step"], "value": mo["value"], "unit": UNIT, "steps": 20,
+                              "kernel_ms": mo["ring_ms_avg"], "frac": ro["frac"], "bound": ro["bound"], "hbm_frac": ro["hbm"]["frac"],
+                              "gpu_launches": mo["launches"], "kernel": mo["cfg"].split(";")[0]}
+            except Exception as ex:  # never lose the headline line to a side measurement
+                others[wl] = {"error": str(ex)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        S, T, B = m["S"], m["T"], m["B"]
         try:
             r = reference_sample(args.workload, steps=3, warmup=1, budget_s=20.0)
             cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
@@ -369,15 +441,17 @@ def main():
             cpu_baseline = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference", "sample": "failed: %s" % ex}
 
     if rank == 0:
+        cfg = m["cfg"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": m["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc, "atoms_total": n_total, "atoms_per_gpu": n_local, "K": Kvec,
-                       "B_live": B, "parallelism": "particle-sharded x%d, per-frame NCCL allreduce of rho(k)" % world,
+            "config": {"workload": args.workload + ": " + m["desc"], "atoms_total": m["n_total"], "atoms_per_gpu": m["n_local"], "K": m["Kvec"],
+                       "B_live": m["B"], "parallelism": "particle-sharded x%d, per-frame NCCL allreduce of rho(k)" % world,
                        "l2": "inputs larger than L2: the origin ring (%s per GPU) is streamed once per frame" % (cfg.split("ring=")[1].split(" ")[0] if "ring=" in cfg else "?"),
-                       "kernel": cfg, "ring_fill_s": t_fill,
-                       "pair_evals_per_sec": value * B},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                       "kernel": cfg, "ring_fill_s": m["t_fill"],
+                       "pair_evals_per_sec": m["value"] * m["B"]},
+            "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["launches"], "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "parity_check": pcheck, "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -156,8 +156,22 @@ int main(int argc, char **argv)
 		exit(1);
 	}
 
+	/* stdout carries exactly the reference's banner lines: whatever NCCL has to say while the communicator is set up (its
+	 * version line under NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE) goes to stderr */
+	int saved_stdout = -1;
+	if (n_gpus > 1) {
+		setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+		fflush(stdout);
+		saved_stdout = dup(STDOUT_FILENO);
+		if (saved_stdout >= 0) dup2(STDERR_FILENO, STDOUT_FILENO);
+	}
 	sqt_multi *h = NULL;
 	int rc = sqt_multi_create(&prm, &h);
+	if (saved_stdout >= 0) {
+		fflush(stdout);
+		dup2(saved_stdout, STDOUT_FILENO);
+		close(saved_stdout);
+	}
 	if (rc) die_engine(NULL, "sqt_multi_create", rc);
 	sqt_results res;
 	if (sqt_results_alloc(&res, deck.nCSpatial, deck.nCTime)) { fputs("Reserving memory Error!!!!!!\n", stdout); exit(1); }

@@ -23,7 +23,7 @@ struct sqt_handle {
 	int S, T, B;
 	int device, n_sm;
 	char err[512];
-	char cfg[768];
+	char cfg[1024];
 	bool flag_f, flag_F, flag_t, flag_V;
 	int ncomp;                // arrays per frame: 3 (x y z) or 6 (+ vx vy vz with -V)
 
@@ -61,6 +61,7 @@ struct sqt_handle {
 	bool latched;
 	int latched_count, latched_limit;
 	int self_kind;            // which kernel serves the per-particle terms: SELF_NONE / SELF_MMA / SELF_VEC / SELF_CLASSIC
+	bool fused;               // small-shape path: rho(k) inside the vector kernel, one kernel finishes the frame (no communicator)
 	KernelChoice kc;
 	MmaChoice mc;             // blocked-Chebyshev / DMMA path for the real slots (large nCSpatial)
 	double *d_mma_partial;
@@ -180,7 +181,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->d_cur[0] = h->d_cur[1] = nullptr; h->h_stage[0] = h->h_stage[1] = nullptr; h->stage_cap = 0;
 	h->copy_pending[0] = h->copy_pending[1] = false; h->stage_next = 0;
 	h->d_ring = nullptr; h->d_partial = nullptr; h->d_tile_ctr = nullptr; h->d_mma_partial = nullptr; h->d_mma_ctr = nullptr;
-	h->mc.on = 0; h->mc.geo = 0; h->vc.on = 0; h->rmc.on = 0; h->self_kind = SELF_NONE;
+	h->mc.on = 0; h->mc.geo = 0; h->vc.on = 0; h->rmc.on = 0; h->self_kind = SELF_NONE; h->fused = false;
 	h->d_rho_partial = nullptr; h->d_mma_extra = h->d_rho_extra = nullptr; h->d_hist_cur = h->d_bufHist = nullptr;
 	h->d_bufFs = h->d_bufF = h->d_bufMSD = h->d_bufMQD = h->d_bufMSDCM = nullptr;
 	h->d_rho0 = h->d_sumr0 = h->d_invL0 = h->d_rho_cur = h->d_cblk = nullptr; h->d_thr = nullptr;
@@ -367,9 +368,12 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 	if (!h->flag_F) h->mc.on = 0;
 	h->vc.on = 0;
 	if (want_self && !h->mc.on && h->mc.geo) { // (rho(k) comes from the tensor-core rho kernel on this path)
-		rc = sqt_pick_vec(h->S, h->flag_F ? h->S : 1, h->B, n_local, h->n_sm, &h->vc);
+		// without a communicator (and without -V) the whole frame is two launches: rho(k) rides in the vector kernel
+		const int fuse = !h->comm && !h->flag_V && h->flag_F;
+		rc = sqt_pick_vec(h->S, h->flag_F ? h->S : 1, h->B, n_local, h->n_sm, fuse, &h->vc);
 		if (rc != 0) return fail(h, SQT_ERR_CUDA, "vector kernel selection failed (rc=%d)", rc);
 	}
+	h->fused = h->vc.on && h->vc.fused;
 	h->self_kind = !want_self ? SELF_NONE : (h->mc.on ? SELF_MMA : (h->vc.on ? SELF_VEC : SELF_CLASSIC));
 	const bool lane_family = h->self_kind == SELF_MMA || h->self_kind == SELF_VEC; // a particle per lane: particle-minor ring
 	// the classic kernel serves its own slots only for SELF_CLASSIC; otherwise at most the six virtual rho(k) slots (B = 0 for it)
@@ -405,7 +409,7 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
 	}
 	h->rmc.on = 0;
-	if (h->self_kind != SELF_CLASSIC || h->flag_V) {
+	if ((h->self_kind != SELF_CLASSIC || h->flag_V) && !h->fused) {
 		const char *rm = getenv("SQT_RHO_MMA");
 		if (!(rm && *rm == '0')) {
 			rc = sqt_pick_rho_mma(h->mc, n_local, h->n_sm, &h->rmc);
@@ -433,29 +437,36 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		}
 	}
 	int off = 0;
+	char classic[400];
+	snprintf(classic, sizeof(classic),
+	         "self_ring_kernel<C=%d,G=%d> persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; %d slot groups x %d warps, "
+	         "%s tiles of %d particles (%d tiles)",
+	         h->kc.C, h->kc.G, h->kc.blocks, h->kc.WPB * 32, h->kc.regs, h->kc.smem, h->kc.occ, h->kc.NWSG, h->kc.KW,
+	         h->kc.dynamic ? "dynamic" : "static", h->kc.tile, h->kc.ntiles);
 	if (h->self_kind == SELF_NONE)
 		off = snprintf(h->cfg, sizeof(h->cfg), "no per-particle kernel (neither -F nor -t); rho(k): ");
 	if (h->self_kind == SELF_VEC)
 		off = snprintf(h->cfg, sizeof(h->cfg),
 		               "self_ring_vec_kernel<C=%d,SPW=%d> (a particle per lane, sums in registers%s) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
-		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
+		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): %s",
 		               h->vc.C, h->vc.SPW, h->flag_F ? "" : "; no -F: MSD / van Hove only", h->vc.blocks, h->vc.WPB * 32, h->vc.regs, h->vc.smem, h->vc.occ, h->vc.NWSG, h->vc.KW,
-		               h->vc.dynamic ? "dynamic" : "static", h->vc.tile);
+		               h->vc.dynamic ? "dynamic" : "static", h->vc.tile,
+		               h->fused ? "six virtual slots of the same kernel, frame finished by vec_finish_kernel (2 launches per frame); unused: " : "");
 	if (h->self_kind == SELF_MMA)
 		off = snprintf(h->cfg, sizeof(h->cfg),
 		               "self_ring_mma_kernel<NT=%d,SPW=%d> (blocked Chebyshev S=%d on DMMA%s) persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; "
 		               "%d slot groups x %d warps, %s tiles of %d particles; + rho(k): ",
 		               h->mc.NT, h->mc.SPW, h->mc.S, h->mc.SPOUT ? ", MSD/MQD outside" : "", h->mc.blocks, h->mc.WPB * 32, h->mc.regs, h->mc.smem, h->mc.occ, h->mc.NWSG, h->mc.KW,
 		               h->mc.dynamic ? "dynamic" : "static", h->mc.tile);
+	if (h->self_kind == SELF_CLASSIC) // the recurrence kernel serves the self terms and, through its six virtual slots, rho(k)
+		off = snprintf(h->cfg, sizeof(h->cfg), "%s%s", classic, h->rmc.on ? "; + rho(k), kvel: " : "");
 	if (h->rmc.on)
-		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles%s; %s: ",
-		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ, h->flag_V ? " (+ velocity-weighted pass, vel_ring_kernel)" : "",
-		                h->self_kind == SELF_CLASSIC ? "self terms" : "unused");
-	snprintf(h->cfg + off, sizeof(h->cfg) - off,
-	         "self_ring_kernel<C=%d,G=%d> persistent grid=%d block=%d regs=%d smem=%zuB occ=%d blocks/SM; %d slot groups x %d warps, "
-	         "%s tiles of %d particles (%d tiles); slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB",
-	         h->kc.C, h->kc.G, h->kc.blocks, h->kc.WPB * 32, h->kc.regs, h->kc.smem, h->kc.occ, h->kc.NWSG, h->kc.KW,
-	         h->kc.dynamic ? "dynamic" : "static", h->kc.tile, h->kc.ntiles, h->B, SQT_NVIRT, ring_bytes / 1e9, (part_bytes + mma_bytes) / 1e6);
+		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles%s",
+		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ, h->flag_V ? " (+ velocity-weighted pass, vel_ring_kernel)" : "");
+	if (h->self_kind != SELF_CLASSIC)
+		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "%s%s", h->rmc.on ? "; unused: " : "", classic);
+	snprintf(h->cfg + off, sizeof(h->cfg) - off, "; slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB", h->B, SQT_NVIRT, ring_bytes / 1e9,
+	         (part_bytes + mma_bytes) / 1e6);
 	h->sized = true;
 	return SQT_OK;
 }
@@ -505,7 +516,53 @@ static int stage_collective(sqt_handle *h, int p, long long n_total, bool split)
 	return SQT_OK;
 }
 
-static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, double xhi)
+// AccumSpacetimeCorr (lmp2sqt.c:376-443) on the host mirror of TBuf.count: kernels for every buffer that completed in this
+// frame (except `done_on_device`, which the fused finish kernel already added), the counters, the PrintProcess latch
+static int accumulate_completed(sqt_handle *h, int done_on_device, int *status)
+{
+	const int S = h->S, T = h->T, B = h->B;
+	const size_t ST = (size_t)S * T;
+	int rc;
+	for (int nb = 0; nb < B; ++nb) {
+		if (h->count[nb] != T) continue;
+		if (nb != done_on_device) {
+			AccumArgs aa;
+			aa.nb = nb; aa.T = T; aa.nCS = S; aa.B = B;
+			aa.bufF = h->d_bufF; aa.bufFs = h->d_bufFs; aa.bufMSD = h->d_bufMSD; aa.bufMQD = h->d_bufMQD; aa.bufMSDCM = h->d_bufMSDCM;
+			aa.bufHist = h->d_bufHist; aa.cblk = h->d_cblk;
+			aa.flag_f = h->flag_f; aa.flag_F = h->flag_F; aa.flag_t = h->flag_t; aa.flag_V = h->flag_V;
+			aa.bufC2 = h->d_bufC2; aa.bufCvv = h->d_bufCvv; aa.bufCvcm = h->d_bufCvcm;
+			for (int i = 0; i < 10; ++i) aa.av[i] = h->d_avblk + (size_t)i * ST;
+			for (int i = 0; i < 5; ++i) aa.av1[i] = h->d_avblk + 10 * ST + (size_t)i * T;
+			rc = sqt_launch_pack(aa, h->s_coll);
+			if (rc) return fail(h, SQT_ERR_CUDA, "buffer_pack_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+			if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * ST + 3 * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
+				return SQT_ERR_NCCL;
+			rc = sqt_launch_accumulate(aa, h->s_coll);
+			if (rc) return fail(h, SQT_ERR_CUDA, "buffer_accumulate_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+			h->launches += 2;
+		}
+		h->count[nb] = 0;
+		++h->countCorrAv;
+		if (h->countCorrAv == h->limitCorrAv) {
+			// PrintProcess (lmp2sqt.c:338-367): latch the sums for the host writers, then
+			// ZeroAvSpacetimeCorr (:366, :477-540) including countCorrAv = 0.
+			CU(cudaMemcpyAsync(h->d_latblk, h->d_avblk, sizeof(double) * h->avblk_n, cudaMemcpyDeviceToDevice, h->s_coll));
+			CU(cudaMemsetAsync(h->d_avblk, 0, sizeof(double) * h->avblk_n, h->s_coll));
+			h->latched = true;
+			h->latched_count = h->countCorrAv;
+			h->latched_limit = h->limitCorrAv;
+			h->countCorrAv = 0;
+			h->n_print++; // Number_call_Print, lmp2sqt.c:674
+			*status = SQT_FLUSH;
+		}
+	}
+	return SQT_OK;
+}
+
+// cur: the frame's SoA on the device, component stride cur_pitch (the engine's own copy of a host frame, or the caller's
+// device buffer of sqt_push_frame_device read in place)
+static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_pitch, long long n_total, double xlo, double xhi)
 {
 	const int S = h->S, T = h->T, B = h->B;
 	h->L = xhi - xlo;                      // lmp2sqt.c:1620
@@ -522,6 +579,51 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	for (int nb = 0; nb < B; ++nb)
 		if (h->count[nb] > 0 && h->h_invL0[nb] != invL) { varbox = 1; break; }
 
+	if (h->fused) {
+		// ---- small shapes, no communicator: two launches per frame -----------------------------------------------------------
+		cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+		if (h->prof) { pe0 = prof_event(h); pe1 = prof_event(h); CU(cudaEventRecord(pe0, h->s_main)); }
+		MmaArgs ma;
+		ma.cur = cur; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = cur_pitch; ma.n_local = h->n_local;
+		ma.tile = h->vc.tile; ma.ntiles = h->vc.ntiles; ma.NWSG = h->vc.NWSG; ma.NWSG_real = h->vc.NWSG_real;
+		ma.KW = h->vc.KW; ma.total_warps = h->vc.total_warps; ma.dynamic = h->vc.dynamic;
+		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = 0; ma.NT = 0; ma.invL = invL;
+		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+		rc = sqt_launch_vec(h->vc, ma, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_vec_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		if (h->prof) CU(cudaEventRecord(pe1, h->s_main));
+		CU(cudaEventRecord(h->ev_ring[slot], h->s_main));
+		int nb_done = -1;
+		for (int nb = 0; nb < B; ++nb) { // ring state machine, lmp2sqt.c:1638-1647
+			if (h->count[nb] == 0) h->h_invL0[nb] = invL;
+			if (++h->count[nb] == T && nb_done < 0) nb_done = nb;
+		}
+		VecFinishArgs fa;
+		MmaReduceArgs &mr = fa.r;
+		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = 0; mr.n_local = h->n_local;
+		mr.KW = h->vc.KW; mr.NWSG = h->vc.NWSG; mr.S = 0; mr.NT = h->vc.C + 2; mr.SPW = h->vc.SPW;
+		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
+		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
+		fa.NWSG_real = h->vc.NWSG_real; fa.rho_cur = h->d_rho_cur; fa.rho0 = h->d_rho0; fa.sumr0 = h->d_sumr0; fa.bufF = h->d_bufF;
+		fa.bufMSDCM = h->d_bufMSDCM; fa.inv_n2 = 1.0 / ((double)n_total * (double)n_total); fa.nb_done = nb_done;
+		fa.flag_f = h->flag_f; fa.flag_F = h->flag_F; fa.flag_t = h->flag_t;
+		const size_t ST = (size_t)S * T;
+		for (int i = 0; i < 7; ++i) fa.av[i] = h->d_avblk + (size_t)i * ST;
+		for (int i = 0; i < 3; ++i) fa.av1[i] = h->d_avblk + 10 * ST + (size_t)i * T;
+		rc = sqt_launch_vec_finish(fa, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "vec_finish_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches += 2;
+		CU(cudaEventRecord(h->ev_rhoc, h->s_main));
+		h->rhoc_pending = true;
+		int status = SQT_OK;
+		rc = accumulate_completed(h, nb_done, &status);
+		if (rc) return rc;
+		h->nSkip = 0;   // lmp2sqt.c:1649
+		h->p_file++;
+		return status;
+	}
+
 	// ---- stage A: rho(k) of this frame first, so that its allreduce, the F(q,t) update and a caller waiting in
 	// sqt_get_rho are not queued behind the (long) self-term kernel -------------------------------------------------
 	if (h->rmc.on) {
@@ -530,14 +632,14 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		cudaEvent_t pe0 = nullptr, pe1 = nullptr;
 		if (h->prof) { pe0 = prof_event(h); pe1 = prof_event(h); CU(cudaEventRecord(pe0, h->s_main)); }
 		RhoMmaArgs qa;
-		qa.cur = h->d_cur[slot]; qa.wt = nullptr; qa.kfac = 0.0; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT;
-		qa.rho_cur = h->d_rho_cur; qa.cur_pitch = h->cur_pitch;
+		qa.cur = cur; qa.wt = nullptr; qa.kfac = 0.0; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT;
+		qa.rho_cur = h->d_rho_cur; qa.cur_pitch = cur_pitch;
 		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.n_sets = h->rmc.blocks; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
 		rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches += 2;
 		if (h->flag_V) { // kvel_q1 (lmp2sqt.c:1203-1208): the same pass with the velocity component as the particle's weight
-			qa.wt = h->d_cur[slot] + 3 * h->cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + h->rho_n;
+			qa.wt = cur + 3 * cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + h->rho_n;
 			rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
 			if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel (velocity-weighted) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 			h->launches += 2;
@@ -552,9 +654,9 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	MmaArgs ma;
 	if (h->self_kind == SELF_MMA || h->self_kind == SELF_VEC) {
 		const bool mm = h->self_kind == SELF_MMA;
-		ma.cur = h->d_cur[slot]; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
-		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = h->cur_pitch; ma.n_local = h->n_local;
-		ma.tile = mm ? h->mc.tile : h->vc.tile; ma.ntiles = mm ? h->mc.ntiles : h->vc.ntiles; ma.NWSG = mm ? h->mc.NWSG : h->vc.NWSG;
+		ma.cur = cur; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = cur_pitch; ma.n_local = h->n_local;
+		ma.tile = mm ? h->mc.tile : h->vc.tile; ma.ntiles = mm ? h->mc.ntiles : h->vc.ntiles; ma.NWSG = mm ? h->mc.NWSG : h->vc.NWSG; ma.NWSG_real = ma.NWSG;
 		ma.KW = mm ? h->mc.KW : h->vc.KW; ma.total_warps = mm ? h->mc.total_warps : h->vc.total_warps; ma.dynamic = mm ? h->mc.dynamic : h->vc.dynamic;
 		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = mm ? h->mc.S : 0; ma.NT = mm ? h->mc.NT : 0; ma.invL = invL;
 		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
@@ -566,8 +668,8 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	const int Bc = h->self_kind == SELF_CLASSIC ? B : 0; // slots the classic kernel treats as real
 	if (classic_launch) {
 		RingArgs ra;
-		ra.cur = h->d_cur[slot]; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
-		ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = h->cur_pitch; ra.n_local = h->n_local;
+		ra.cur = cur; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
+		ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = cur_pitch; ra.n_local = h->n_local;
 		ra.tile = h->kc.tile; ra.ntiles = h->kc.ntiles; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
 		ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = Bc; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
 		ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
@@ -582,8 +684,8 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
 	if (h->d_vring) { // -V -t: rrCvv over the origin-velocity ring (lmp2sqt.c:1397-1401, 1441)
 		VelArgs va;
-		va.vcur = h->d_cur[slot] + 3 * h->cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
-		va.cur_pitch = h->cur_pitch; va.RP = h->ring_np; va.n_local = h->n_local; va.nchunk = h->vel_nchunk; va.chunk = h->vel_chunk;
+		va.vcur = cur + 3 * cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
+		va.cur_pitch = cur_pitch; va.RP = h->ring_np; va.n_local = h->n_local; va.nchunk = h->vel_nchunk; va.chunk = h->vel_chunk;
 		va.p = p; va.T = T; va.B = B;
 		rc = sqt_launch_vel(va, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "vel_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -625,41 +727,9 @@ static int run_frame(sqt_handle *h, int slot, long long n_total, double xlo, dou
 		if (h->count[nb] == 0) h->h_invL0[nb] = invL;
 		++h->count[nb];
 	}
-	// ---- AccumSpacetimeCorr, lmp2sqt.c:376-443 ---------------------------------------------
 	int status = SQT_OK;
-	const size_t ST = (size_t)S * T;
-	for (int nb = 0; nb < B; ++nb) {
-		if (h->count[nb] != T) continue;
-		AccumArgs aa;
-		aa.nb = nb; aa.T = T; aa.nCS = S; aa.B = B;
-		aa.bufF = h->d_bufF; aa.bufFs = h->d_bufFs; aa.bufMSD = h->d_bufMSD; aa.bufMQD = h->d_bufMQD; aa.bufMSDCM = h->d_bufMSDCM;
-		aa.bufHist = h->d_bufHist; aa.cblk = h->d_cblk;
-		aa.flag_f = h->flag_f; aa.flag_F = h->flag_F; aa.flag_t = h->flag_t; aa.flag_V = h->flag_V;
-		aa.bufC2 = h->d_bufC2; aa.bufCvv = h->d_bufCvv; aa.bufCvcm = h->d_bufCvcm;
-		for (int i = 0; i < 10; ++i) aa.av[i] = h->d_avblk + (size_t)i * ST;
-		for (int i = 0; i < 5; ++i) aa.av1[i] = h->d_avblk + 10 * ST + (size_t)i * T;
-		rc = sqt_launch_pack(aa, h->s_coll);
-		if (rc) return fail(h, SQT_ERR_CUDA, "buffer_pack_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * ST + 3 * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
-			return SQT_ERR_NCCL;
-		rc = sqt_launch_accumulate(aa, h->s_coll);
-		if (rc) return fail(h, SQT_ERR_CUDA, "buffer_accumulate_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches += 2;
-		h->count[nb] = 0;
-		++h->countCorrAv;
-		if (h->countCorrAv == h->limitCorrAv) {
-			// PrintProcess (lmp2sqt.c:338-367): latch the sums for the host writers, then
-			// ZeroAvSpacetimeCorr (:366, :477-540) including countCorrAv = 0.
-			CU(cudaMemcpyAsync(h->d_latblk, h->d_avblk, sizeof(double) * h->avblk_n, cudaMemcpyDeviceToDevice, h->s_coll));
-			CU(cudaMemsetAsync(h->d_avblk, 0, sizeof(double) * h->avblk_n, h->s_coll));
-			h->latched = true;
-			h->latched_count = h->countCorrAv;
-			h->latched_limit = h->limitCorrAv;
-			h->countCorrAv = 0;
-			h->n_print++; // Number_call_Print, lmp2sqt.c:674
-			status = SQT_FLUSH;
-		}
-	}
+	rc = accumulate_completed(h, -1, &status);
+	if (rc) return rc;
 	if (split) { CU(cudaEventRecord(h->ev_coll, h->s_coll)); h->coll_pending = true; }
 	h->nSkip = 0;   // lmp2sqt.c:1649
 	h->p_file++;
@@ -686,18 +756,20 @@ static int push_common(sqt_handle *h, const double *const *comp, bool on_device,
 	if (on_device) {
 		// engine-owned copy, so the producer may refill its buffer.  Ordering against the producer: the legacy default stream
 		// synchronises with the engine's (blocking) streams by itself; any other producer stream is named by the caller
+		// The kernels read the caller's buffer in place (component stride n_local): no engine-side copy.  Ordering against the
+		// producer: the legacy default stream synchronises with the engine's (blocking) streams by itself, both ways; any other
+		// producer stream is named by the caller and is made to wait, after the frame's kernels, before it may refill d_soa
 		slot = h->stage_next; h->stage_next ^= 1;
 		if (producer_stream) {
 			CU(cudaEventRecord(h->ev_prod, (cudaStream_t)producer_stream));
 			CU(cudaStreamWaitEvent(h->s_main, h->ev_prod, 0));
 		}
-		int rc = sqt_launch_soa_copy(h->d_cur[slot], h->cur_pitch, comp[0], n_local, n_local, h->ncomp, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "soa_copy launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-		if (producer_stream) {
+		const int rcf = run_frame(h, slot, comp[0], n_local, n_total, xlo, xhi);
+		if (rcf >= 0 && producer_stream) {
 			CU(cudaEventRecord(h->ev_prod, h->s_main));
 			CU(cudaStreamWaitEvent((cudaStream_t)producer_stream, h->ev_prod, 0));
 		}
+		return rcf;
 	} else {
 		const double *src[6];
 		for (int a = 0; a < h->ncomp; ++a) src[a] = comp[a];
@@ -726,7 +798,7 @@ static int push_common(sqt_handle *h, const double *const *comp, bool on_device,
 		h->copy_pending[slot] = true;
 		CU(cudaStreamWaitEvent(h->s_main, h->ev_copy[slot], 0));
 	}
-	return run_frame(h, slot, n_total, xlo, xhi);
+	return run_frame(h, slot, h->d_cur[slot], h->cur_pitch, n_total, xlo, xhi);
 }
 
 extern "C" int sqt_push_frame(sqt_handle *h, const double *soa, int n_local, long long n_total, double xlo, double xhi)
@@ -915,6 +987,7 @@ extern "C" int sqt_comm_init(sqt_handle *h, const void *id, int rank, int nranks
 {
 	if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return SQT_ERR_ARG;
 	if (h->comm) return fail(h, SQT_ERR_STATE, "communicator already attached");
+	if (h->sized && nranks > 1) return fail(h, SQT_ERR_STATE, "attach the communicator before the first frame (the kernel configuration depends on it)");
 	if (nranks == 1) return SQT_OK;
 	CU(cudaSetDevice(h->device));
 	if (sqt_comm_create(&h->comm, id, rank, nranks, h->err, sizeof(h->err))) return SQT_ERR_NCCL;

@@ -56,6 +56,7 @@ struct MmaArgs {
 	const long long *thr;     // [nCS+2]
 	long long cur_pitch;
 	int n_local, tile, ntiles, NWSG, KW, total_warps, dynamic;
+	int NWSG_real;            // vector kernel, fused small-shape path: slot groups >= NWSG_real serve the six virtual rho(k) slots
 	int p, T, B, nCS;
 	long long RP;
 	int S, NT;                // stride of the block decomposition, column tiles (8 NT >= S + 2)
@@ -85,11 +86,25 @@ int sqt_launch_mma_reduce(const MmaReduceArgs &a, cudaStream_t st);
 struct VecChoice {
 	int on;
 	int C, SPW, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // C = nCSpatial rounded up to 4
+	int fused, NWSG_real;     // fused: rho(k) rides in the same kernel (six virtual slots) and ONE kernel finishes the frame
 	size_t smem;
 };
 // nChain = recurrence steps per (particle, origin, axis): nCSpatial, or 1 when F_s is not wanted (-f / -t without -F): the
 // kernel then only serves MSD, MQD and the van Hove histogram, whatever nCSpatial is
-int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, VecChoice *vc);
+int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, int fuse, VecChoice *vc);
+// the fused frame epilogue of the small-shape path (no communicator): per origin slot the fixed-order sum of the per-warp
+// rows, rho(k) from the virtual slots' rows, the F(q,t) update / origin copies / MSDCM of collective_ring_kernel, and
+// AccumSpacetimeCorr for the buffer that completes in this frame
+struct VecFinishArgs {
+	MmaReduceArgs r;          // as for vec_reduce_kernel (NT = row width C + 2)
+	int NWSG_real;
+	double *rho_cur, *rho0, *sumr0, *bufF, *bufMSDCM;
+	double inv_n2;
+	int nb_done;              // buffer completing in this frame (-1: none)
+	int flag_f, flag_F, flag_t;
+	double *av[7], *av1[3];
+};
+int sqt_launch_vec_finish(const VecFinishArgs &a, cudaStream_t st);
 int sqt_launch_vec(const VecChoice &vc, const MmaArgs &a, cudaStream_t st);
 int sqt_launch_vec_reduce(const MmaReduceArgs &a, cudaStream_t st);
 

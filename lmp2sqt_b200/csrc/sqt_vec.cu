@@ -33,13 +33,17 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 	for (int e = threadIdx.x; e < nCS * SB; e += blockDim.x) s_hist[e] = 0;
 	for (int e = threadIdx.x; e < nCS + 2; e += blockDim.x) s_thr[e] = a.thr[e];
 
+	// fused small-shape path: the slot groups beyond NWSG_real serve the six virtual rho(k) slots (axis x {cos, sin}) -- the
+	// reference's own tables summed over particles (lmp2sqt.c:1176-1217), one chain per slot, no ring, no histogram
+	const bool virt = wsg >= a.NWSG_real;
+	const int v0 = (wsg - a.NWSG_real) * SPW;
 	unsigned live_m = 0, cap_m = 0;
 #pragma unroll
 	for (int s = 0; s < SPW; ++s) {
 		int tau = 0;
-		const bool lv = slot0 + s < a.B && mma_slot_state(slot0 + s, a.p, a.T, a.B, &tau);
+		const bool lv = virt ? (v0 + s < SQT_NVIRT) : (slot0 + s < a.B && mma_slot_state(slot0 + s, a.p, a.T, a.B, &tau));
 		if (lv) live_m |= 1u << s;
-		if (lv && tau == 0) cap_m |= 1u << s;
+		if (!virt && lv && tau == 0) cap_m |= 1u << s;
 	}
 	const double invL = a.invL;
 	double acc[SPW][C], msd[SPW], mqd[SPW];
@@ -77,6 +81,28 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 				const bool valid = i0 + lane < tlen;
 				const long long n = tbase + (valid ? i0 + lane : tlen - 1);
 				const double rx = __ldg(cx + n), ry = __ldg(cy + n), rz = __ldg(cz + n);
+				if (virt) {
+#pragma unroll
+					for (int s = 0; s < SPW; ++s) {
+						if (!((live_m >> s) & 1)) continue;
+						const int ax = (v0 + s) >> 1, im = (v0 + s) & 1;
+						const double xa = ax == 0 ? rx : (ax == 1 ? ry : rz);
+						const double u = xa * invL;
+						const double c = mma_cos2pi(u);
+						double x = im ? mma_cos2pi(u - 0.25) : c;  // sin(k x) / cos(k x): the seeds of lmp2sqt.c:1180-1186
+						double pv = im ? 0.0 : 1.0;                 // x_0 = sin 0 / cos 0
+						if (!valid) { x = 0.0; pv = 0.0; }
+						const double t = c + c;
+#pragma unroll
+						for (int m = 0; m < C; ++m) {
+							acc[s][m] += x;
+							const double nx = fma(t, x, -pv);
+							pv = x; x = nx;
+						}
+						if (!im && valid) msd[s] += xa;            // the cos slots also carry sum_n r_a (for MSDCM)
+					}
+					continue;
+				}
 				double *rrow = a.ring + (long long)slot0 * 3 * RP + n; // [slot][axis][particle]
 #pragma unroll
 				for (int s = 0; s < SPW; ++s) {
@@ -141,7 +167,7 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 		if (cntv) {
 			const int col = e / nCS;
 			const int gwc = blockIdx.x * wpb + col / SPW;
-			const int sl = (gwc % a.NWSG) * SPW + col % SPW;
+			const int sl = (gwc % a.NWSG) * SPW + col % SPW; // (virtual slot groups never count: cntv is 0 there)
 			atomicAdd(&a.hist_cur[sl * nCS + e % nCS], cntv);
 		}
 	}
@@ -177,6 +203,109 @@ __global__ void vec_reduce_kernel(const MmaReduceArgs a)
 		for (int i = threadIdx.x; i < a.NWSG; i += blockDim.x) a.tile_ctr[i] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// vec_finish_kernel: everything after the particle loop of a frame in ONE launch, for the small shapes (shipped decks:
+// 4,000 / 32,000 atoms, nCSpatial 30 / 10) whose frames are a few tens of microseconds and were dominated by the launch
+// latency of five tiny kernels.  One block per origin slot; every block also reduces the six virtual rows to rho(k) for
+// itself (the same loads in the same order in every block: identical bits, no inter-block dependency), then does for its
+// slot what collective_ring_kernel does, and the block of the buffer that completes in this frame runs AccumSpacetimeCorr
+// (lmp2sqt.c:368-444).  Only without a communicator: sharded runs need the allreduces in between.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) vec_finish_kernel(const VecFinishArgs a)
+{
+	extern __shared__ double s_fin[]; // rho [6 nCS] + sum r [3]
+	const MmaReduceArgs &r = a.r;
+	const int slot = blockIdx.x;
+	const int W = r.NT, SPW = r.SPW, nCS = r.nCS, T = r.T;
+	double *s_rho = s_fin;
+	int tau = 0;
+	const bool live = mma_slot_state(slot, r.p, r.T, r.B, &tau);
+	const int wsg = slot / SPW, s = slot % SPW;
+	if (live) { // vec_reduce_kernel's part
+		for (int m = threadIdx.x; m < W; m += blockDim.x) {
+			const double *p = r.partial + ((long long)(wsg * r.KW) * SPW + s) * W + m;
+			const double v = strided_sum(p, (long long)SPW * W, 0, r.KW, 1);
+			if (m == W - 2) r.bufMSD[slot * T + tau] = v;
+			else if (m == W - 1) r.bufMQD[slot * T + tau] = v;
+			else if (m < nCS) r.bufFs[((long long)slot * T + tau) * nCS + m] = v;
+		}
+		if (threadIdx.x == 0 && tau == 0) r.invL0[slot] = r.invL;
+		for (int bin = threadIdx.x; bin < nCS; bin += blockDim.x)
+			r.bufHist[((long long)slot * T + tau) * nCS + bin] = r.hist_cur[slot * nCS + bin];
+	}
+	// rho(k) from the virtual slots' rows: virtual slot v = 2 axis + {cos, sin} sits in group NWSG_real + v / SPW
+	for (int e = threadIdx.x; e < SQT_NVIRT * nCS + 3; e += blockDim.x) {
+		int v, m;
+		if (e < SQT_NVIRT * nCS) { v = e / nCS; m = e % nCS; } else { v = 2 * (e - SQT_NVIRT * nCS); m = W - 2; } // sum_n r_a: the cos slots' MSD column
+		const double *p = r.partial + ((long long)((a.NWSG_real + v / SPW) * r.KW) * SPW + v % SPW) * W + m;
+		const double val = strided_sum(p, (long long)SPW * W, 0, r.KW, 1);
+		if (e < SQT_NVIRT * nCS) s_rho[(2 * nCS) * (v >> 1) + 2 * m + (v & 1)] = val; // marker layout lmp2sqt.c:1173-1174
+		else s_rho[6 * nCS + (e - SQT_NVIRT * nCS)] = val;
+	}
+	__syncthreads();
+	for (int bin = threadIdx.x; bin < nCS; bin += blockDim.x) r.hist_cur[slot * nCS + bin] = 0;
+	if (slot == 0) {
+		for (int e = threadIdx.x; e < 6 * nCS + 3; e += blockDim.x) a.rho_cur[e] = s_rho[e];
+		for (int i = threadIdx.x; i < r.NWSG; i += blockDim.x) r.tile_ctr[i] = 0;
+	}
+	if (!live) return;
+	// collective_ring_kernel's part for this slot (lmp2sqt.c:1584-1586, 1298-1299, 1447-1450)
+	const bool capture = tau == 0;
+	for (int m = threadIdx.x; m < nCS; m += blockDim.x) {
+		double F = 0.0;
+		double *r0 = a.rho0 + (long long)slot * 6 * nCS;
+		for (int ax = 0; ax < 3; ++ax) {
+			const int mR = (2 * nCS) * ax + 2 * m, mI = mR + 1;
+			const double R = s_rho[mR], I = s_rho[mI];
+			if (capture) { r0[mR] = R; r0[mI] = I; }
+			const double R0 = capture ? R : r0[mR], I0 = capture ? I : r0[mI];
+			F = __dadd_rn(F, __dadd_rn(__dmul_rn(R, R0), __dmul_rn(I, I0)));
+		}
+		a.bufF[((long long)slot * T + tau) * nCS + m] = F;
+	}
+	if (threadIdx.x == 0) {
+		const double *sr = s_rho + 6 * nCS;
+		double *s0 = a.sumr0 + slot * 3;
+		if (capture) { s0[0] = sr[0]; s0[1] = sr[1]; s0[2] = sr[2]; }
+		const double ex = capture ? 0.0 : sr[0] - s0[0], ey = capture ? 0.0 : sr[1] - s0[1], ez = capture ? 0.0 : sr[2] - s0[2];
+		double d = __dmul_rn(ex, ex);
+		d = __dadd_rn(d, __dmul_rn(ey, ey));
+		d = __dadd_rn(d, __dmul_rn(ez, ez));
+		a.bufMSDCM[slot * T + tau] += d * a.inv_n2; // never zeroed: cumulative over buffer reuse, like the reference
+	}
+	if (slot != a.nb_done) return;
+	// AccumSpacetimeCorr for this buffer: its last lag was written by this very block just above
+	__syncthreads();
+	const int TS = T * nCS;
+	const long long base = (long long)slot * TS;
+	for (int idx = threadIdx.x; idx < TS; idx += blockDim.x) {
+		const int nk = idx / T, nt = idx % T, src = nt * nCS + nk; // output [nk][nt] like avF_qq2, buffers [lag][nk]
+		if (a.flag_f) {
+			const double F = a.bufF[base + src];
+			a.av[0][idx] += F; a.av[1][idx] += F * F;
+			if (a.flag_F) {
+				const double Fs = r.bufFs[base + src];
+				const double Fd = 2.0 * (F - Fs);
+				a.av[2][idx] += Fs; a.av[3][idx] += Fs * Fs;
+				a.av[4][idx] += Fd; a.av[5][idx] += Fd * Fd;
+			}
+			if (a.flag_t) a.av[6][idx] += (double)r.bufHist[base + src];
+		}
+	}
+	if (a.flag_t)
+		for (int idx = threadIdx.x; idx < T; idx += blockDim.x) {
+			a.av1[0][idx] += r.bufMSD[slot * T + idx];
+			a.av1[1][idx] += r.bufMQD[slot * T + idx];
+			a.av1[2][idx] += a.bufMSDCM[slot * T + idx];
+		}
+}
+
+int sqt_launch_vec_finish(const VecFinishArgs &a, cudaStream_t st)
+{
+	vec_finish_kernel<<<a.r.B, 128, sizeof(double) * (6 * a.r.nCS + 3), st>>>(a);
+	return (int)cudaGetLastError();
+}
+
 typedef void (*vec_fn)(const MmaArgs);
 static vec_fn vec_variant(int C, int SPW, int varbox)
 {
@@ -193,9 +322,9 @@ static int vec_env_int(const char *name, int dflt)
 	return (s && *s) ? atoi(s) : dflt;
 }
 
-int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, VecChoice *vc)
+int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, int fuse, VecChoice *vc)
 {
-	vc->on = 0;
+	vc->on = 0; vc->fused = 0;
 	const int want = vec_env_int("SQT_VEC", -1);
 	if (want == 0 || B < 1 || nCS < 1 || nChain < 1 || nChain > 32) return 0;
 	const int C = (nChain + 3) / 4 * 4;
@@ -213,7 +342,9 @@ int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, VecChoice *v
 	cudaFuncAttributes fa;
 	cudaFuncGetAttributes(&fa, (const void *)vec_variant(C, SPW, 0));
 	vc->C = C; vc->SPW = SPW; vc->WPB = W; vc->occ = occ; vc->regs = fa.numRegs; vc->smem = sm;
-	vc->NWSG = (B + SPW - 1) / SPW;
+	vc->NWSG_real = (B + SPW - 1) / SPW;
+	vc->fused = fuse && C >= nCS && vec_env_int("SQT_FUSE", 1) != 0; // the virtual rho slots need all nCSpatial chains
+	vc->NWSG = vc->NWSG_real + (vc->fused ? (SQT_NVIRT + SPW - 1) / SPW : 0);
 	int blocks = n_sm * occ;
 	long long warps_per_group = ((long long)blocks * W + vc->NWSG - 1) / vc->NWSG;
 	long long ts = n_local / (4 * warps_per_group); // about 4 tiles per warp, a multiple of 32, 32 .. 256 particles

@@ -34,8 +34,10 @@ def _digest(t) -> str:
     return h.hexdigest()
 
 
+@pytest.mark.parametrize("fuse", ["1", "0"])   # two launches per frame (rho(k) inside the vector kernel + vec_finish_kernel) / separate kernels
 @pytest.mark.parametrize("name,want_kernel", [("c1_shape", "self_ring_vec_kernel<C=32"), ("c2_shape", "self_ring_vec_kernel<C=12")])
-def test_baseline_shapes_match_the_reference(name, want_kernel):
+def test_baseline_shapes_match_the_reference(monkeypatch, name, want_kernel, fuse):
+    monkeypatch.setenv("SQT_FUSE", fuse)
     """BASELINE config 1 (4,000 atoms, nCSpatial 30, 150/150, 320 frames) and config 2's shape (32,000 atoms, nCSpatial 10,
     150/150, 200-frame prefix): raw sums of the unmodified reference, single thread (lmp2sqt.c:1477-1591, 1368-1460)."""
     g = dict(np.load(os.path.join(LARGE, name + ".npz")))
@@ -45,6 +47,7 @@ def test_baseline_shapes_match_the_reference(name, want_kernel):
     ref = {k[4:]: (v.item() if v.shape == () else v) for k, v in g.items() if k.startswith("raw_")}
     res, eng = run_trajectories([traj], Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T), "Ft")
     assert eng.kernel_config.startswith(want_kernel), eng.kernel_config
+    assert ("vec_finish_kernel" in eng.kernel_config) == (fuse == "1"), eng.kernel_config
     got = res.to_dict()
     # the closed form of the ring bookkeeping: 320 frames at 150/150 -> 171 completed buffers
     assert got["countCorrAv"] == ref["countCorrAv"] == sum(max(0, (n_frames - (nb * T) // B) // T) for nb in range(B))

@@ -21,15 +21,19 @@ def _run_both(trajs, S, T, B, skip=0, flags="Ft", rVal=0.2):
     return got, raw, eng, log
 
 
+@pytest.mark.parametrize("fuse", ["1", "0"])   # nCSpatial <= 32 on one GPU: fused two-launch frame, or the separate kernels
 @pytest.mark.parametrize("S,T,B,ncell,frames", [
     (4, 10, 5, 2, 40),      # the smoke shape
     (10, 30, 30, 3, 100),   # smallQ-like, B == T
     (30, 12, 4, 2, 50),     # in.lmp2sqt.150's nCSpatial (C=30 kernel)
     (7, 9, 9, 2, 31),       # odd sizes, padded chains
+    (13, 7, 7, 3, 30),      # one slot per warp (C = 16) with an odd slot count
 ])
-def test_ring_matches_oracle(S, T, B, ncell, frames):
+def test_ring_matches_oracle(monkeypatch, S, T, B, ncell, frames, fuse):
+    monkeypatch.setenv("SQT_FUSE", fuse)
     traj = synth.make_trajectory(n_cells=ncell, n_frames=frames, seed=11)
     got, raw, eng, _ = _run_both([traj], S, T, B)
+    assert ("vec_finish_kernel" in eng.kernel_config) == (fuse == "1"), eng.kernel_config
     check_raw_sums(got, raw, traj.n_atoms, label="S%d T%d B%d " % (S, T, B))
     fd_identity(got)
 

@@ -32,7 +32,7 @@ def _check_velocity(got, raw, label):
     (5, 8, 4, 2, 32, 40, "self_ring_vec_kernel"),          # the committed -V fixture's shape
     (30, 10, 10, 5, 500, 35, "self_ring_vec_kernel"),      # in.lmp2sqt.150's nCSpatial
     (43, 6, 6, 4, 200, 20, "self_ring_kernel<C=43"),       # recurrence kernel: positions ring slot-minor, velocity ring particle-minor
-    (70, 8, 8, 4, 300, 30, "self_ring_mma_kernel"),
+    (70, 8, 8, 5, 300, 30, "self_ring_mma_kernel"),
     (171, 6, 6, 8, 2000, 16, "self_ring_mma_kernel"),      # config 5's nCSpatial, several particle tiles
     (256, 4, 4, 3, 100, 12, "self_ring_mma_kernel"),       # the largest nCSpatial -V takes
 ])
@@ -43,6 +43,7 @@ def test_velocity_correlators_match_oracle(S, T, B, ncell, n_atoms, frames, want
     assert eng.kernel_config.startswith(want) and "velocity-weighted" in eng.kernel_config, eng.kernel_config
     got = res.to_dict()
     _, raw, _ = pyoracle.run_port(traj, S, T, B, limitCorrAv=BIG, flags="FtV", finish=False)
+    assert traj.n_atoms == n_atoms
     check_raw_sums(got, raw, n_atoms, label="V S%d " % S)     # everything -V does not touch is unchanged
     _check_velocity(got, raw, "S%d " % S)
     eng.close()

@@ -23,11 +23,16 @@ def test_product_tree_never_touches_the_oracle():
     assert not bad, bad
 
 
-def test_bench_uses_the_oracle_only_in_its_cpu_baseline_legs():
+def test_bench_uses_the_oracle_only_as_checker_and_cpu_baseline():
+    """bench.py touches oracle/ in two functions only: reference_sample (the cpu_baseline key and --impl reference: the
+    reference's CPU code is the thing timed there) and parity_check (the oracle as the CHECKER of a small sharded run,
+    before anything is timed).  Nothing that produces `value` or `e2e` may."""
     src = open(os.path.join(ROOT, "bench.py")).read()
     funcs = re.split(r"\ndef ", src)
     users = [f.split("(")[0] for f in funcs if "pyoracle" in f]
-    assert users and set(users) <= {"reference_sample"}, users   # called by the cpu_baseline key and by --impl reference
+    assert users and set(users) <= {"reference_sample", "parity_check"}, users
+    timed = [f for f in funcs if f.startswith("time_workload(")]
+    assert len(timed) == 1 and "oracle" not in timed[0]
 
 
 def test_kernels_are_built_for_sm_100a_only():
