@@ -119,6 +119,15 @@ int sqt_analysis_fourier(sqt_analysis *a, int window);
 int sqt_analysis_print(const sqt_analysis *a, const char *outdir);
 void sqt_analysis_free(sqt_analysis *a);
 
+/* ---- the TEXT post-processor (reference: analysis.c:138-536 = AverageFqt2FqOrFt.c:135-507), on output.txt ---------------
+ * Same struct (Dc / Hc stay unused).  The reference's stale row parse is kept: the first nCSpatial numbers of a row are
+ * taken, so column 0 of the density blocks is the time.  "-" reads stdin. */
+int sqt_analysis_text_load(sqt_analysis *a, const char *deck_path, const char *txt_path, int nSetSkip);
+int sqt_analysis_text_time(sqt_analysis *a, int nValDiff, const char *outdir);       /* :370-455; also prints the "nv = ..." line */
+int sqt_analysis_text_fourier(sqt_analysis *a, int window);                          /* :349-368 */
+/* Fqt, GammaQT, Dqt, D0Hqt, Fqt1 `.<block>.info` at %9.4e, and Print_R2_data's echo on stdout (:458-536) */
+int sqt_analysis_text_print(const sqt_analysis *a, const char *outdir);
+
 #ifdef __cplusplus
 }
 #endif

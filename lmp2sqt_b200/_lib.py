@@ -13,6 +13,7 @@ ENGINE_SO = os.path.join(PKG_DIR, "libsqt_b200.so")
 HOST_SO = os.path.join(PKG_DIR, "libsqt_host.so")
 CLI_BIN = os.path.join(PKG_DIR, "bin", "lmp2sqt_b200.out")
 ANALYSIS_BIN = os.path.join(PKG_DIR, "bin", "analysis_binary_b200.out")
+ANALYSIS_TEXT_BIN = os.path.join(PKG_DIR, "bin", "analysis_b200.out")
 
 SQT_OK, SQT_FLUSH = 0, 1
 SQT_COMM_ID_BYTES = 128
@@ -139,6 +140,10 @@ HOST_API = [
     ("sqt_analysis_fourier", C.c_int, [C.POINTER(SqtAnalysis), C.c_int]),
     ("sqt_analysis_print", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p]),
     ("sqt_analysis_free", None, [C.POINTER(SqtAnalysis)]),
+    ("sqt_analysis_text_load", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p, C.c_char_p, C.c_int]),
+    ("sqt_analysis_text_time", C.c_int, [C.POINTER(SqtAnalysis), C.c_int, C.c_char_p]),
+    ("sqt_analysis_text_fourier", C.c_int, [C.POINTER(SqtAnalysis), C.c_int]),
+    ("sqt_analysis_text_print", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p]),
 ]
 
 

@@ -248,6 +248,33 @@ __global__ void __launch_bounds__(128) vec_finish_kernel(const VecFinishArgs a)
 		for (int e = threadIdx.x; e < 6 * nCS + 3; e += blockDim.x) a.rho_cur[e] = s_rho[e];
 		for (int i = threadIdx.x; i < r.NWSG; i += blockDim.x) r.tile_ctr[i] = 0;
 	}
+	// AccumSpacetimeCorr (lmp2sqt.c:368-444) for the buffer that completes in this frame, part 1: its lags < T - 1 were
+	// written in earlier frames, so all blocks share them (one element per thread); lag T - 1 follows below, by the block
+	// that writes it
+	const int nbd = a.nb_done;
+	if (nbd >= 0) {
+		const int TS = T * nCS;
+		const long long base = (long long)nbd * TS;
+		for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TS; idx += gridDim.x * blockDim.x) {
+			const int nk = idx / T, nt = idx % T, src = nt * nCS + nk; // output [nk][nt] like avF_qq2, buffers [lag][nk]
+			if (nt == T - 1 || !a.flag_f) continue;
+			const double F = a.bufF[base + src];
+			a.av[0][idx] += F; a.av[1][idx] += F * F;
+			if (a.flag_F) {
+				const double Fs = r.bufFs[base + src];
+				const double Fd = 2.0 * (F - Fs);
+				a.av[2][idx] += Fs; a.av[3][idx] += Fs * Fs;
+				a.av[4][idx] += Fd; a.av[5][idx] += Fd * Fd;
+			}
+			if (a.flag_t) a.av[6][idx] += (double)r.bufHist[base + src];
+		}
+		if (a.flag_t && blockIdx.x == gridDim.x - 1)
+			for (int idx = threadIdx.x; idx < T - 1; idx += blockDim.x) {
+				a.av1[0][idx] += r.bufMSD[nbd * T + idx];
+				a.av1[1][idx] += r.bufMQD[nbd * T + idx];
+				a.av1[2][idx] += a.bufMSDCM[nbd * T + idx];
+			}
+	}
 	if (!live) return;
 	// collective_ring_kernel's part for this slot (lmp2sqt.c:1584-1586, 1298-1299, 1447-1450)
 	const bool capture = tau == 0;
@@ -273,14 +300,14 @@ __global__ void __launch_bounds__(128) vec_finish_kernel(const VecFinishArgs a)
 		d = __dadd_rn(d, __dmul_rn(ez, ez));
 		a.bufMSDCM[slot * T + tau] += d * a.inv_n2; // never zeroed: cumulative over buffer reuse, like the reference
 	}
-	if (slot != a.nb_done) return;
-	// AccumSpacetimeCorr for this buffer: its last lag was written by this very block just above
+	if (slot != nbd) return;
+	// part 2: the last lag of the completing buffer, written by this very block just above
 	__syncthreads();
-	const int TS = T * nCS;
+	const int TS = T * nCS, nt = T - 1;
 	const long long base = (long long)slot * TS;
-	for (int idx = threadIdx.x; idx < TS; idx += blockDim.x) {
-		const int nk = idx / T, nt = idx % T, src = nt * nCS + nk; // output [nk][nt] like avF_qq2, buffers [lag][nk]
-		if (a.flag_f) {
+	if (a.flag_f)
+		for (int nk = threadIdx.x; nk < nCS; nk += blockDim.x) {
+			const int idx = nk * T + nt, src = nt * nCS + nk;
 			const double F = a.bufF[base + src];
 			a.av[0][idx] += F; a.av[1][idx] += F * F;
 			if (a.flag_F) {
@@ -291,13 +318,11 @@ __global__ void __launch_bounds__(128) vec_finish_kernel(const VecFinishArgs a)
 			}
 			if (a.flag_t) a.av[6][idx] += (double)r.bufHist[base + src];
 		}
+	if (a.flag_t && threadIdx.x == 0) {
+		a.av1[0][nt] += r.bufMSD[slot * T + nt];
+		a.av1[1][nt] += r.bufMQD[slot * T + nt];
+		a.av1[2][nt] += a.bufMSDCM[slot * T + nt];
 	}
-	if (a.flag_t)
-		for (int idx = threadIdx.x; idx < T; idx += blockDim.x) {
-			a.av1[0][idx] += r.bufMSD[slot * T + idx];
-			a.av1[1][idx] += r.bufMQD[slot * T + idx];
-			a.av1[2][idx] += a.bufMSDCM[slot * T + idx];
-		}
 }
 
 int sqt_launch_vec_finish(const VecFinishArgs &a, cudaStream_t st)

@@ -29,6 +29,7 @@ PORT_SO = os.path.join(HERE, "libsqt_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "liblmp2sqt_ref.so")
 REF_BIN = os.path.join(HERE, "_ref", "lmp2sqt_ref.out")
 REF_ANALYSIS_BIN = os.path.join(HERE, "_ref", "analysis_binary_ref.out")
+REF_ANALYSIS_TEXT_BIN = os.path.join(HERE, "_ref", "analysis_ref.out")   # analysis.c (= AverageFqt2FqOrFt.c), reads output.txt
 
 NAMES2D = ["avF", "StdDevF", "avF_s", "StdDevF_s", "avF_d", "StdDevF_d", "avDrTable"]
 NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv"]
@@ -41,7 +42,7 @@ def build(force: bool = False) -> None:
     """Compile the restatement (always possible) and, where /root/reference exists, the reference."""
     if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(HERE, "sqt_oracle.c")):
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
-    if os.path.exists("/root/reference/lmp2sqt.c") and (force or not os.path.exists(REF_SO)):
+    if os.path.exists("/root/reference/lmp2sqt.c") and (force or not os.path.exists(REF_SO) or not os.path.exists(REF_ANALYSIS_TEXT_BIN)):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 

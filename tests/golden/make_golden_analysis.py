@@ -83,7 +83,62 @@ def main():
             with open(os.path.join(out, case, m + ".json"), "w") as f:
                 json.dump(files, f, indent=0, sort_keys=True)
             print(case, m, len(files), "files")
+    main_text(here)
+
+
+# ---- the TEXT post-processor (analysis.c = AverageFqt2FqOrFt.c, built into oracle/_ref as analysis_ref.out) on output.txt ----
+TEXT_MODES = {"t": [], "t_d2": ["-d", "2"], "f": ["-f"], "fw": ["-f", "-w"]}
+
+
+def run_ref_text(indir, args):
+    with tempfile.TemporaryDirectory() as td:
+        shutil.copy(os.path.join(indir, "in.lmp2sqt"), td)
+        shutil.copy(os.path.join(indir, "output.txt"), td)
+        r = subprocess.run([pyoracle.REF_ANALYSIS_TEXT_BIN, *args, "output.txt"], cwd=td, capture_output=True, text=True)
+        assert r.returncode == 0, (indir, args, r.returncode)
+        d = {f: open(os.path.join(td, f)).read() for f in sorted(os.listdir(td)) if f.endswith(".info") or f.endswith(".out")}
+        d["<stdout>"] = r.stdout
+        return d
+
+
+def main_text(here):
+    """analysis_text/<case>/in.lmp2sqt, output.txt (written by the reference lmp2sqt) and <mode>.json = every file the
+    reference text post-processor wrote, plus its stdout."""
+    out = os.path.join(here, "analysis_text")
+    shutil.rmtree(out, ignore_errors=True)
+    cases = {}
+    for case, src, modes in (("g5", "g5_ring30", ["t", "t_d2"]), ("g2", "g2_final_print", ["t"]), ("g4_f_only", "g4_collective_only", ["t"])):
+        d = os.path.join(out, case)
+        os.makedirs(d)
+        shutil.copy(os.path.join(here, src, "in.lmp2sqt.after"), os.path.join(d, "in.lmp2sqt"))
+        shutil.copy(os.path.join(here, src, "output.txt"), d)
+        cases[case] = modes
+    # nCTime 9 (2 (nCTime - 1) a power of two: the frequency domain), two sets concatenated
+    d = os.path.join(out, "t9_two_sets")
+    os.makedirs(d)
+    with tempfile.TemporaryDirectory() as td:
+        texts = []
+        for seed in (31, 32):
+            t = synth.make_trajectory(n_cells=2, n_frames=50, seed=seed)
+            synth.write_text_dump(t, os.path.join(td, "dump.lammpstrj"))
+            synth.write_deck(os.path.join(td, "in.lmp2sqt"), limitCorrAv=0, nCBuffer=3, nCSpatial=5, nCTime=9)
+            r = pyoracle.run_reference_cli(td, "in.lmp2sqt", ["dump.lammpstrj"])
+            assert r.returncode == 0
+            texts.append(open(os.path.join(td, "output.txt")).read())
+        shutil.copy(os.path.join(td, "in.lmp2sqt"), d)
+        open(os.path.join(d, "output.txt"), "w").write(texts[0] + texts[1])
+    cases["t9_two_sets"] = ["t", "f", "fw"]
+    for case, modes in cases.items():
+        for m in modes:
+            files = run_ref_text(os.path.join(out, case), TEXT_MODES[m])
+            with open(os.path.join(out, case, m + ".json"), "w") as f:
+                json.dump(files, f, indent=0, sort_keys=True)
+            print("text", case, m, len(files), "files")
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["text"]:
+        pyoracle.build()
+        main_text(os.path.dirname(os.path.abspath(__file__)))
+    else:
+        main()

@@ -137,3 +137,101 @@ def test_from_results_equals_the_file_route(tmp_path):
     assert sorted(os.listdir(o1)) == sorted(os.listdir(o2)) and len(os.listdir(o1)) == 30
     for f in os.listdir(o1):
         _same_text((o2 / f).read_text(), (o1 / f).read_text(), f)
+
+
+# ---- the TEXT post-processor (reference: analysis.c = AverageFqt2FqOrFt.c), on output.txt: SURVEY.md section 8f.2, second half ----
+GOLD_TEXT = os.path.join(HERE, "golden", "analysis_text")
+TEXT_MODES = {"t": [], "t_d2": ["-d", "2"], "f": ["-f"], "fw": ["-f", "-w"]}
+TEXT_CASES = [("g5", "t"), ("g5", "t_d2"), ("g2", "t"), ("g4_f_only", "t"), ("t9_two_sets", "t"), ("t9_two_sets", "f"), ("t9_two_sets", "fw")]
+
+
+def _same_text_but_heap_garbage(got: str, want: str, name: str):
+    """Token equality; NaN signs aside.  One more exemption: when the very first decay test of wave number 1 fails, the
+    reference reads the word in FRONT of its table (analysis.c:421-425 with ppT = -1: malloc bookkeeping, a denormal) and
+    derives one Gamma / D entry from its logarithm; here that word is 0.  Such tokens are a denormal in the reference's file,
+    or stand where ours is +-inf / nan because log(0) went in."""
+    g, w = got.split(), want.split()
+    assert len(g) == len(w), name
+    odd = 0
+    for a, b in zip(g, w):
+        if a == b or ("nan" in a and "nan" in b):
+            continue
+        try:
+            fb = float(b)
+        except ValueError:
+            raise AssertionError((name, a, b))
+        if (abs(fb) < 1e-300 and float(a) == 0.0) or a.lstrip("-") in ("inf", "nan"):
+            odd += 1
+            continue
+        raise AssertionError((name, a, b))
+    assert odd <= 4, (name, odd)          # one element per derived table of one block, never more
+
+
+def _run_text_cli(exe, case, mode, tmp_path):
+    d = tmp_path / (case + "_" + mode)
+    d.mkdir()
+    for f in ("in.lmp2sqt", "output.txt"):
+        shutil.copy(os.path.join(GOLD_TEXT, case, f), d)
+    r = subprocess.run([exe, *TEXT_MODES[mode], "output.txt"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    out = {f: (d / f).read_text() for f in sorted(os.listdir(d)) if f.endswith(".info") or f.endswith(".out")}
+    out["<stdout>"] = r.stdout
+    return out
+
+
+@pytest.mark.parametrize("case,mode", TEXT_CASES)
+def test_text_cli_writes_the_reference_files(tmp_path, case, mode):
+    """bin/analysis_b200.out against what the unmodified analysis.c wrote for the same output.txt (files AND stdout),
+    including its stale row parse (column 0 of the density blocks is the time) and the `-f`-only file whose self / cross
+    blocks carry no rows."""
+    want = json.load(open(os.path.join(GOLD_TEXT, case, mode + ".json")))
+    got = _run_text_cli(_lib.ANALYSIS_TEXT_BIN, case, mode, tmp_path)
+    assert sorted(got) == sorted(want)
+    for f in want:
+        _same_text_but_heap_garbage(got[f], want[f], f)
+    if case == "g5":                                   # a case without the out-of-table read: byte for byte
+        for f in want:
+            _same_text(got[f], want[f], f)
+
+
+@pytest.mark.skipif(not os.path.exists(pyoracle.REF_ANALYSIS_TEXT_BIN), reason="oracle/_ref/analysis_ref.out not built")
+def test_text_cli_matches_live_reference_on_a_fresh_run(tmp_path):
+    t = synth.make_trajectory(n_cells=3, n_atoms=70, n_frames=80, seed=37)
+    src = tmp_path / "src"
+    src.mkdir()
+    synth.write_text_dump(t, str(src / "dump.lammpstrj"))
+    synth.write_deck(str(src / "in.lmp2sqt"), limitCorrAv=0, nCBuffer=17, nCSpatial=7, nCTime=17, nCSkip=1)
+    assert pyoracle.run_reference_cli(str(src), "in.lmp2sqt", ["dump.lammpstrj"]).returncode == 0
+    for args in ([], ["-f"], ["-f", "-w"], ["-d", "6"]):
+        outs = {}
+        for tag, exe in (("ref", pyoracle.REF_ANALYSIS_TEXT_BIN), ("ours", _lib.ANALYSIS_TEXT_BIN)):
+            d = tmp_path / (tag + "".join(args))
+            d.mkdir()
+            shutil.copy(src / "in.lmp2sqt", d)
+            shutil.copy(src / "output.txt", d)
+            r = subprocess.run([exe, *args, "output.txt"], cwd=d, capture_output=True, text=True)
+            assert r.returncode == 0
+            outs[tag] = {f: (d / f).read_text() for f in sorted(os.listdir(d)) if f.endswith(".info") or f.endswith(".out")}
+            outs[tag]["<stdout>"] = r.stdout
+        assert sorted(outs["ref"]) == sorted(outs["ours"]) and len(outs["ours"]) >= 17
+        for f in outs["ref"]:
+            _same_text_but_heap_garbage(outs["ours"][f], outs["ref"][f], f)
+
+
+def test_text_post_processor_reads_our_own_output_txt(tmp_path):
+    """The chain a user of the reference runs (BASELINE config 5's tail): results -> output.txt (our writers, byte-identical to
+    the reference's on the golden cases, tests/test_host.py) -> text post-processor -> Fqt.* tables that carry the parsed
+    columns.  Checks the documented stale parse: column k of Fqt.full-density is output.txt's k-th number of each row."""
+    case = os.path.join(GOLD_TEXT, "g5")
+    d = tmp_path / "run"
+    d.mkdir()
+    for f in ("in.lmp2sqt", "output.txt"):
+        shutil.copy(os.path.join(case, f), d)
+    assert subprocess.run([_lib.ANALYSIS_TEXT_BIN, "output.txt"], cwd=d, capture_output=True).returncode == 0
+    rows = [ln.split() for ln in (d / "output.txt").read_text().split("\n")[2:32]]           # 30 lags of the full-density block
+    tab = [ln.split() for ln in (d / "Fqt.full-density.info").read_text().strip().split("\n")[1:]]
+    S = 10
+    for t, r in enumerate(tab):
+        assert len(r) == S + 1
+        for k in range(S):
+            assert float(r[1 + k]) == pytest.approx(float(rows[t][k]), rel=1e-4, abs=1e-12)       # %9.4e of the k-th number of the row
