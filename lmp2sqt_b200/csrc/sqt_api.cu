@@ -402,8 +402,8 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		                     : sizeof(double) * (size_t)h->vc.NWSG * h->vc.KW * h->vc.SPW * (h->vc.C + 2);
 		CU(cudaMalloc(&h->d_mma_partial, mma_bytes));
 		CU(cudaMemsetAsync(h->d_mma_partial, 0, mma_bytes, h->s_main));
-		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * nwsg));
-		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * nwsg, h->s_main));
+		CU(cudaMalloc(&h->d_mma_ctr, sizeof(int) * 2 * nwsg)); // tile counters, then the fused path's rows-posted counters
+		CU(cudaMemsetAsync(h->d_mma_ctr, 0, sizeof(int) * 2 * nwsg, h->s_main));
 		const size_t xb = h->mc.on ? sizeof(double) * (size_t)h->mc.NWSG * h->mc.KW * h->mc.SPW * 2 : 16;
 		CU(cudaMalloc(&h->d_mma_extra, xb));
 		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
@@ -590,6 +590,7 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		ma.KW = h->vc.KW; ma.total_warps = h->vc.total_warps; ma.dynamic = h->vc.dynamic;
 		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = 0; ma.NT = 0; ma.invL = invL;
 		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+		ma.done_ctr = h->d_mma_ctr + h->vc.NWSG; ma.bufFs = h->d_bufFs; ma.bufMSD = h->d_bufMSD; ma.bufMQD = h->d_bufMQD; ma.rho_cur = h->d_rho_cur;
 		rc = sqt_launch_vec(h->vc, ma, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_vec_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		if (h->prof) CU(cudaEventRecord(pe1, h->s_main));
@@ -605,7 +606,7 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		mr.KW = h->vc.KW; mr.NWSG = h->vc.NWSG; mr.S = 0; mr.NT = h->vc.C + 2; mr.SPW = h->vc.SPW;
 		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
 		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
-		fa.NWSG_real = h->vc.NWSG_real; fa.rho_cur = h->d_rho_cur; fa.rho0 = h->d_rho0; fa.sumr0 = h->d_sumr0; fa.bufF = h->d_bufF;
+		fa.NWSG_real = h->vc.NWSG_real; fa.done_ctr = h->d_mma_ctr + h->vc.NWSG; fa.rho_cur = h->d_rho_cur; fa.rho0 = h->d_rho0; fa.sumr0 = h->d_sumr0; fa.bufF = h->d_bufF;
 		fa.bufMSDCM = h->d_bufMSDCM; fa.inv_n2 = 1.0 / ((double)n_total * (double)n_total); fa.nb_done = nb_done;
 		fa.flag_f = h->flag_f; fa.flag_F = h->flag_F; fa.flag_t = h->flag_t;
 		const size_t ST = (size_t)S * T;
@@ -660,6 +661,7 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		ma.KW = mm ? h->mc.KW : h->vc.KW; ma.total_warps = mm ? h->mc.total_warps : h->vc.total_warps; ma.dynamic = mm ? h->mc.dynamic : h->vc.dynamic;
 		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = mm ? h->mc.S : 0; ma.NT = mm ? h->mc.NT : 0; ma.invL = invL;
 		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+		ma.done_ctr = nullptr; ma.bufFs = ma.bufMSD = ma.bufMQD = ma.rho_cur = nullptr;
 		rc = mm ? sqt_launch_mma(h->mc, ma, h->s_main) : sqt_launch_vec(h->vc, ma, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "self_ring_mma_kernel" : "self_ring_vec_kernel", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;

@@ -57,6 +57,10 @@ struct MmaArgs {
 	long long cur_pitch;
 	int n_local, tile, ntiles, NWSG, KW, total_warps, dynamic;
 	int NWSG_real;            // vector kernel, fused small-shape path: slot groups >= NWSG_real serve the six virtual rho(k) slots
+	// fused small-shape path only (done_ctr != nullptr): the LAST warp of a slot group to finish sums the group's per-warp
+	// rows (fixed order, whichever warp it is) and writes them where the reference keeps them
+	int *done_ctr;            // [NWSG] warps of the group that have posted their rows (re-armed by vec_finish_kernel)
+	double *bufFs, *bufMSD, *bufMQD, *rho_cur;
 	int p, T, B, nCS;
 	long long RP;
 	int S, NT;                // stride of the block decomposition, column tiles (8 NT >= S + 2)
@@ -98,6 +102,7 @@ int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, int fuse, Ve
 struct VecFinishArgs {
 	MmaReduceArgs r;          // as for vec_reduce_kernel (NT = row width C + 2)
 	int NWSG_real;
+	int *done_ctr;
 	double *rho_cur, *rho0, *sumr0, *bufF, *bufMSDCM;
 	double inv_n2;
 	int nb_done;              // buffer completing in this frame (-1: none)

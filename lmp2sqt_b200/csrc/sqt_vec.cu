@@ -161,6 +161,40 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 			}
 		}
 	}
+	if (a.done_ctr) {
+		// fused small-shape path: whichever warp of this slot group posts its rows last also sums the group's rows -- in row
+		// order, so the result does not depend on which warp that is -- and writes them to their final place: F_s / MSD / MQD
+		// of the slot's current lag (TBuf.F_s_qq2, rrMSD, rrMQD), or rho(k) and sum_n r_a for a virtual group
+		__threadfence();
+		int last = 0;
+		if (lane == 0) last = atomicAdd(&a.done_ctr[wsg], 1) == nws - 1;
+		last = __shfl_sync(0xffffffffu, last, 0);
+		if (last) {
+			__threadfence();
+			const long long stride = (long long)SPW * (C + 2);
+#pragma unroll
+			for (int s = 0; s < SPW; ++s) {
+				const double *p0 = a.partial + ((long long)(wsg * a.KW) * SPW + s) * (C + 2);
+				if (virt) {
+					const int v = v0 + s;
+					if (v >= SQT_NVIRT) continue;
+					const int ax = v >> 1, im = v & 1;
+					for (int m = lane; m < nCS; m += 32) a.rho_cur[(2 * nCS) * ax + 2 * m + im] = strided_sum(p0 + m, stride, 0, nws, 1); // marker layout lmp2sqt.c:1173-1174
+					if (!im && lane == 0) a.rho_cur[6 * nCS + ax] = strided_sum(p0 + C, stride, 0, nws, 1);
+				} else {
+					const int slot = slot0 + s;
+					int tau = 0;
+					if (slot >= a.B || !mma_slot_state(slot, a.p, a.T, a.B, &tau)) continue;
+					for (int m = lane; m < C + 2; m += 32) {
+						const double v = strided_sum(p0 + m, stride, 0, nws, 1);
+						if (m == C) a.bufMSD[slot * a.T + tau] = v;
+						else if (m == C + 1) a.bufMQD[slot * a.T + tau] = v;
+						else if (m < nCS) a.bufFs[((long long)slot * a.T + tau) * nCS + m] = v;
+					}
+				}
+			}
+		}
+	}
 	__syncthreads();
 	for (int e = threadIdx.x; e < nCS * SB; e += blockDim.x) {
 		const int cntv = s_hist[e];
@@ -206,48 +240,34 @@ __global__ void vec_reduce_kernel(const MmaReduceArgs a)
 // ---------------------------------------------------------------------------------------------
 // vec_finish_kernel: everything after the particle loop of a frame in ONE launch, for the small shapes (shipped decks:
 // 4,000 / 32,000 atoms, nCSpatial 30 / 10) whose frames are a few tens of microseconds and were dominated by the launch
-// latency of five tiny kernels.  One block per origin slot; every block also reduces the six virtual rows to rho(k) for
-// itself (the same loads in the same order in every block: identical bits, no inter-block dependency), then does for its
-// slot what collective_ring_kernel does, and the block of the buffer that completes in this frame runs AccumSpacetimeCorr
-// (lmp2sqt.c:368-444).  Only without a communicator: sharded runs need the allreduces in between.
+// latency of five tiny kernels.  One block per origin slot: it moves the slot's van Hove counts to their lag, does for its
+// slot what collective_ring_kernel does, and AccumSpacetimeCorr (lmp2sqt.c:368-444) for the buffer that completes in this
+// frame is shared by all blocks.  (The sums over the per-warp rows -- F_s, MSD, MQD, rho(k) -- are made by the last warp of
+// each slot group inside self_ring_vec_kernel.)  Only without a communicator: sharded runs need the allreduces in between.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) vec_finish_kernel(const VecFinishArgs a)
 {
 	extern __shared__ double s_fin[]; // rho [6 nCS] + sum r [3]
 	const MmaReduceArgs &r = a.r;
 	const int slot = blockIdx.x;
-	const int W = r.NT, SPW = r.SPW, nCS = r.nCS, T = r.T;
+	const int nCS = r.nCS, T = r.T;
 	double *s_rho = s_fin;
 	int tau = 0;
 	const bool live = mma_slot_state(slot, r.p, r.T, r.B, &tau);
-	const int wsg = slot / SPW, s = slot % SPW;
-	if (live) { // vec_reduce_kernel's part
-		for (int m = threadIdx.x; m < W; m += blockDim.x) {
-			const double *p = r.partial + ((long long)(wsg * r.KW) * SPW + s) * W + m;
-			const double v = strided_sum(p, (long long)SPW * W, 0, r.KW, 1);
-			if (m == W - 2) r.bufMSD[slot * T + tau] = v;
-			else if (m == W - 1) r.bufMQD[slot * T + tau] = v;
-			else if (m < nCS) r.bufFs[((long long)slot * T + tau) * nCS + m] = v;
-		}
+	// rho(k), sum_n r_a, F_s, MSD and MQD of this frame are final already: the last warp of every slot group of
+	// self_ring_vec_kernel summed the group's rows
+	for (int e = threadIdx.x; e < 6 * nCS + 3; e += blockDim.x) s_rho[e] = a.rho_cur[e];
+	if (live) {
 		if (threadIdx.x == 0 && tau == 0) r.invL0[slot] = r.invL;
-		for (int bin = threadIdx.x; bin < nCS; bin += blockDim.x)
+		for (int bin = threadIdx.x; bin < nCS; bin += blockDim.x) {
 			r.bufHist[((long long)slot * T + tau) * nCS + bin] = r.hist_cur[slot * nCS + bin];
-	}
-	// rho(k) from the virtual slots' rows: virtual slot v = 2 axis + {cos, sin} sits in group NWSG_real + v / SPW
-	for (int e = threadIdx.x; e < SQT_NVIRT * nCS + 3; e += blockDim.x) {
-		int v, m;
-		if (e < SQT_NVIRT * nCS) { v = e / nCS; m = e % nCS; } else { v = 2 * (e - SQT_NVIRT * nCS); m = W - 2; } // sum_n r_a: the cos slots' MSD column
-		const double *p = r.partial + ((long long)((a.NWSG_real + v / SPW) * r.KW) * SPW + v % SPW) * W + m;
-		const double val = strided_sum(p, (long long)SPW * W, 0, r.KW, 1);
-		if (e < SQT_NVIRT * nCS) s_rho[(2 * nCS) * (v >> 1) + 2 * m + (v & 1)] = val; // marker layout lmp2sqt.c:1173-1174
-		else s_rho[6 * nCS + (e - SQT_NVIRT * nCS)] = val;
-	}
+			r.hist_cur[slot * nCS + bin] = 0;
+		}
+	} else
+		for (int bin = threadIdx.x; bin < nCS; bin += blockDim.x) r.hist_cur[slot * nCS + bin] = 0;
+	if (slot == 0)
+		for (int i = threadIdx.x; i < r.NWSG; i += blockDim.x) { r.tile_ctr[i] = 0; a.done_ctr[i] = 0; } // re-arm the scheduler
 	__syncthreads();
-	for (int bin = threadIdx.x; bin < nCS; bin += blockDim.x) r.hist_cur[slot * nCS + bin] = 0;
-	if (slot == 0) {
-		for (int e = threadIdx.x; e < 6 * nCS + 3; e += blockDim.x) a.rho_cur[e] = s_rho[e];
-		for (int i = threadIdx.x; i < r.NWSG; i += blockDim.x) r.tile_ctr[i] = 0;
-	}
 	// AccumSpacetimeCorr (lmp2sqt.c:368-444) for the buffer that completes in this frame, part 1: its lags < T - 1 were
 	// written in earlier frames, so all blocks share them (one element per thread); lag T - 1 follows below, by the block
 	// that writes it
