@@ -54,11 +54,14 @@ typedef struct {
 	int device;          /* CUDA device ordinal this handle owns (sqt_create); first device of sqt_multi_create */
 	int n_gpus;          /* sqt_multi_create: GPUs device .. device + n_gpus - 1, particle-sharded in this process; 0 = 1 */
 	int flag_V;          /* -V (flag_velocity, lmp2sqt.c:172): current correlators; frames then carry vx vy vz */
-	int reserved[5];     /* must be zero */
+	int flag_M;          /* -M (flag_magnet, :177): dipole-weighted density kmu_q1 and its correlators; frames then carry mux muy muz */
+	int flag_s;          /* -s (flag_s, :156-160; switches flag_t on like getopt does): per-axis MSD and the stress-like
+	                      * squared change of sum_n v (x) r; frames then carry vx vy vz */
+	int reserved[3];     /* must be zero */
 } sqt_params;
 
 /* Largest nCSpatial the kernels cover (the reference accepts any; a deck beyond this is refused by sqt_create).  With
- * flag_V the limit is 256 (the current density comes from the tensor-core rho(k) kernel). */
+ * flag_V or flag_M the limit is 256 (the weighted densities come from the tensor-core rho(k) kernel). */
 #define SQT_MAX_NCSPATIAL 1024
 #define SQT_MAX_NCSPATIAL_V 256
 
@@ -84,6 +87,13 @@ typedef struct {
 	 * rrCvcmvcmAv [nCTime] (:423-426) */
 	double *avC2_v_rho, *avC2_rho_v, *avC2_v_v;
 	double *rrCvvAv, *rrCvcmvcmAv;
+	/* -M only: avC2_mu_rho, avC2_rho_mu, avC2_mu_mu, and with -V as well avC2_v_mu, avC2_mu_v (lmp2sqt.c:399-407);
+	 * rrCmmAv [nCTime] stays zero: the reference allocates, zeroes and prints it but never adds to it (:420-432) */
+	double *avC2_v_mu, *avC2_mu_v, *avC2_mu_rho, *avC2_rho_mu, *avC2_mu_mu;
+	double *rrCmmAv;
+	/* -s only: rrMSR1_R_Av [nCTime][3] (x y z) and rrMSR2_VR_Av [nCTime][9] (xx xy xz yx yy yz zx zy zz), the reference's
+	 * VecR3 / Rank2R3 arrays (:427-432) */
+	double *rrMSR1_R_Av, *rrMSR2_VR_Av;
 } sqt_results;
 
 int  sqt_results_alloc(sqt_results *r, int nCSpatial, int nCTime);
@@ -104,7 +114,7 @@ int  sqt_begin_file(sqt_handle *h);
 
 /* ---- frames ------------------------------------------------------------------------------ */
 /* Pinned host staging for the next frame, SoA: x[0..n), y[0..n), z[0..n) as doubles
- * (3*n_atoms_local contiguous; with flag_V six arrays: x y z vx vy vz).  Double buffered: the pointer stays valid
+ * (3*n_atoms_local contiguous; then vx vy vz with flag_V or flag_s, then mux muy muz with flag_M: sqt_frame_components arrays).  Double buffered: the pointer stays valid
  * until the second following sqt_stage_acquire.  Blocks only if the slot's previous H2D copy is still in flight. */
 double *sqt_stage_acquire(sqt_handle *h, int n_atoms_local);
 
@@ -121,6 +131,12 @@ int  sqt_push_frame(sqt_handle *h, const double *soa, int n_atoms_local, long lo
  * flag_V).  Pinned memory is copied asynchronously and must stay unmodified until two further pushes or sqt_sync. */
 int  sqt_push_frame_xyz(sqt_handle *h, const double *x, const double *y, const double *z, const double *vx, const double *vy,
                         const double *vz, int n_atoms_local, long long n_atoms_total, double xlo, double xhi);
+/* ... and with the dipole components (unit vectors as the reference's reader leaves them, snapshot.c:440-459; needed with flag_M) */
+int  sqt_push_frame_xyz_vm(sqt_handle *h, const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                           const double *vz, const double *mux, const double *muy, const double *muz, int n_atoms_local,
+                           long long n_atoms_total, double xlo, double xhi);
+/* Arrays per frame the handle expects in SoA frames: 3, 6 or 9 (x y z [vx vy vz] [mux muy muz]). */
+int  sqt_frame_components(const sqt_handle *h);
 /* Same, for a frame already resident in device memory (SoA, 3*n_atoms_local doubles; 6*n with flag_V) on
  * the handle's device -- the binary / on-device frame source path.
  * Stream ordering: the engine copies d_soa on its own (blocking) stream.  A producer that fills d_soa on the legacy
@@ -153,6 +169,8 @@ int  sqt_number_call_print(const sqt_handle *h);
 int  sqt_get_rho(sqt_handle *h, double *out);
 /* With flag_V: the current density kvel_q1 of the last processed frame, same layout (lmp2sqt.c:1203-1208). */
 int  sqt_get_kvel(sqt_handle *h, double *out);
+/* With flag_M: kmu_q1 (lmp2sqt.c:1209-1214). */
+int  sqt_get_kmu(sqt_handle *h, double *out);
 long long sqt_kernel_launches(const sqt_handle *h);       /* launches of OUR kernels so far */
 /* CUDA-event timing of a frame's dominant kernels on their own stream: the self-term kernel of the family in
  * use (self_ring_mma_kernel / self_ring_vec_kernel / self_ring_kernel) plus the rho(k) kernel, one event pair around
@@ -189,7 +207,8 @@ int  sqt_multi_n_gpus(const sqt_multi *m);
 sqt_handle *sqt_multi_handle(sqt_multi *m, int rank);      /* introspection only */
 int  sqt_multi_set_limit(sqt_multi *m, int limitCorrAv);
 int  sqt_multi_begin_file(sqt_multi *m);
-/* pinned (portable) SoA for a whole frame: x[n] y[n] z[n] (+ vx[n] vy[n] vz[n] with flag_V); double buffered */
+/* pinned (portable) SoA for a whole frame: x[n] y[n] z[n] (+ vx[n] vy[n] vz[n] with flag_V / flag_s, + mux[n] muy[n] muz[n] with
+ * flag_M); double buffered */
 double *sqt_multi_stage_acquire(sqt_multi *m, int n_atoms);
 int  sqt_multi_push_frame(sqt_multi *m, const double *soa, int n_atoms, double xlo, double xhi);
 int  sqt_multi_fetch_results(sqt_multi *m, sqt_results *out);

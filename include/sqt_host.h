@@ -77,6 +77,10 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 /* -V: the same with the velocity columns of the `id type xu yu zu vx vy vz` style (snapshot.c:285-300).  Any other style
  * fails the frame: the reference would correlate uninitialised memory there (make_atom / make_atom_dipole never set vx). */
 int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz);
+/* -M: also the dipole columns of the `id type xu yu zu mux muy muz [vx vy vz]` styles, normalised to unit vectors like
+ * make_atom_dipole does (snapshot.c:440-459).  With mux != NULL, velocities (vx != NULL) come from the 11-column style only. */
+int sqt_reader_read_atoms_vm(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz,
+                             double *mux, double *muy, double *muz);
 int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd);
 
 /* factorDr[nr], lmp2sqt.c:1987-2009, from what the engine recorded at the first processed frame. */
@@ -89,6 +93,12 @@ void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int fla
  * lmp2sqt.c:127-132).  Returns 0 or -1. */
 int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t,
                            const char *date);
+/* All getopt flags of the reference (lmp2sqt.c:152-191) in one struct: -f -F -t -V -M -s.  F implies f, s implies t. */
+typedef struct { int f, F, t, V, M, s; } sqt_flags;
+/* prePrintProcess / PrintProcess for any flag set: with -M also the C2_mu_* (and with -V C2_v_mu / C2_mu_v) files and the Cmm
+ * column of the Dt file, with -s the Stress%03d.info.<date> file and the msdx msdy msdz columns (lmp2sqt.c:933-1076). */
+void sqt_host_normalise_x(sqt_results *r, const sqt_deck *d, const sqt_flags *fl);
+int sqt_host_print_process_x(const char *dir, sqt_results *r, const sqt_deck *d, const sqt_flags *fl, const char *date);
 /* The same with -V: also normalises the current correlators and writes C2_v_v / C2_v_rho / C2_rho_v%03d.info.<date> and the
  * Cvv, Cvcmvcm columns of the Dt file (lmp2sqt.c:933-993, 1033-1076). */
 int sqt_host_print_process_v(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V,

@@ -23,7 +23,12 @@ class SqtParams(C.Structure):
     _fields_ = [("kVal", C.c_double), ("deltaT", C.c_double), ("mass", C.c_double), ("rVal", C.c_double),
                 ("limitCorrAv", C.c_int), ("nCBuffer", C.c_int), ("nCSpatial", C.c_int), ("nCTime", C.c_int),
                 ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int),
-                ("device", C.c_int), ("n_gpus", C.c_int), ("flag_V", C.c_int), ("reserved", C.c_int * 5)]
+                ("device", C.c_int), ("n_gpus", C.c_int), ("flag_V", C.c_int), ("flag_M", C.c_int), ("flag_s", C.c_int),
+                ("reserved", C.c_int * 3)]
+
+
+class SqtFlags(C.Structure):
+    _fields_ = [("f", C.c_int), ("F", C.c_int), ("t", C.c_int), ("V", C.c_int), ("M", C.c_int), ("s", C.c_int)]
 
 
 _PD = C.POINTER(C.c_double)
@@ -36,7 +41,9 @@ class SqtResults(C.Structure):
                 ("avF_qq2", _PD), ("StdDevF_qq2", _PD), ("avF_s_qq2", _PD), ("StdDevF_s_qq2", _PD),
                 ("avF_d_qq2", _PD), ("StdDevF_d_qq2", _PD), ("avDrTable", _PD),
                 ("rrMSDAv", _PD), ("rrMQDAv", _PD), ("rrMSDCMAv", _PD),
-                ("avC2_v_rho", _PD), ("avC2_rho_v", _PD), ("avC2_v_v", _PD), ("rrCvvAv", _PD), ("rrCvcmvcmAv", _PD)]
+                ("avC2_v_rho", _PD), ("avC2_rho_v", _PD), ("avC2_v_v", _PD), ("rrCvvAv", _PD), ("rrCvcmvcmAv", _PD),
+                ("avC2_v_mu", _PD), ("avC2_mu_v", _PD), ("avC2_mu_rho", _PD), ("avC2_rho_mu", _PD), ("avC2_mu_mu", _PD),
+                ("rrCmmAv", _PD), ("rrMSR1_R_Av", _PD), ("rrMSR2_VR_Av", _PD)]
 
 
 class SqtDeck(C.Structure):
@@ -72,6 +79,8 @@ ENGINE_API = [
     ("sqt_stage_acquire", C.c_void_p, [C.c_void_p, C.c_int]),
     ("sqt_push_frame", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double]),
     ("sqt_push_frame_xyz", C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int, C.c_longlong, C.c_double, C.c_double]),
+    ("sqt_push_frame_xyz_vm", C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_int, C.c_longlong, C.c_double, C.c_double]),
+    ("sqt_frame_components", C.c_int, [C.c_void_p]),
     ("sqt_push_frame_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double]),
     ("sqt_push_frame_device_ex", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_void_p]),
     ("sqt_fetch_results", C.c_int, [C.c_void_p, C.POINTER(SqtResults)]),
@@ -82,6 +91,7 @@ ENGINE_API = [
     ("sqt_number_call_print", C.c_int, [C.c_void_p]),
     ("sqt_get_rho", C.c_int, [C.c_void_p, C.c_void_p]),
     ("sqt_get_kvel", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("sqt_get_kmu", C.c_int, [C.c_void_p, C.c_void_p]),
     ("sqt_kernel_launches", C.c_longlong, [C.c_void_p]),
     ("sqt_profile_enable", C.c_int, [C.c_void_p, C.c_int]),
     ("sqt_profile_read", C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
@@ -129,11 +139,14 @@ HOST_API = [
     ("sqt_reader_read_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("sqt_reader_skip_atoms", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)]),
     ("sqt_reader_read_atoms_v", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)] + [C.c_void_p] * 6),
+    ("sqt_reader_read_atoms_vm", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader)] + [C.c_void_p] * 9),
     ("sqt_host_factor_dr", None, [C.POINTER(SqtResults), C.c_double, C.c_void_p]),
     ("sqt_host_normalise", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int]),
     ("sqt_host_print_process", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_char_p]),
     ("sqt_host_normalise_v", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_int]),
     ("sqt_host_print_process_v", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    ("sqt_host_normalise_x", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.POINTER(SqtFlags)]),
+    ("sqt_host_print_process_x", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.POINTER(SqtFlags), C.c_char_p]),
     ("sqt_analysis_load", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p, C.c_char_p, C.c_int]),
     ("sqt_analysis_from_results", C.c_int, [C.POINTER(SqtAnalysis), C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int]),
     ("sqt_analysis_time", C.c_int, [C.POINTER(SqtAnalysis), C.c_int, C.c_double, C.c_char_p]),

@@ -4,8 +4,11 @@
  * two-pass file handling and limitCorrAv bookkeeping as the reference's main (lmp2sqt.c:117-336);
  * the per-frame work goes through the C-ABI of include/sqt.h to the GPU engine.
  *
- * -V (velocity / current correlators, lmp2sqt.c:172) is served too; -s (stress) and -M (magnet) are outside the hot
- * path and are rejected with a message instead of silently computing something else.
+ * -V (velocity / current correlators, lmp2sqt.c:172), -M (dipole-density correlators, :177) and -s (per-axis MSD and the
+ * stress-like correlator, :156-160) are served too.  Which dump style carries what follows the
+ * reference's reader: velocities come from `id type xu yu zu vx vy vz`, dipoles from `... mux muy muz [vx vy vz]`
+ * (snapshot.c:263-331); asking for both reads the 11-column style in full, which the reference's reader never does
+ * (its 11-column branch is shadowed by the 8-column dipole test, :262 vs :308).
  *
  * Extension: `-g N` (or SQT_GPUS=N) shards every frame by particle over N GPUs of this box (devices SQT_DEVICE ..
  * SQT_DEVICE + N - 1): one reader thread, one pinned frame, N asynchronous chunk copies.
@@ -33,7 +36,7 @@ static void die_engine(sqt_multi *m, const char *what, int rc)
 
 int main(int argc, char **argv)
 {
-	bool flag_f = false, flag_F = false, flag_t = false, flag_d = false, flag_V = false;
+	bool flag_f = false, flag_F = false, flag_t = false, flag_d = false, flag_V = false, flag_M = false, flag_s = false;
 	char inputFilename[512] = "in.lmp2sqt"; /* lmp2sqt.c:108 */
 	int device = 0, n_gpus = 1;
 	const char *dev_env = getenv("SQT_DEVICE");
@@ -49,9 +52,9 @@ int main(int argc, char **argv)
 	         "		-F) collective self calculation required long time and large memory \n"
 	         "			space-time, twotime, stress etc...\n"
 	         "		-t) only twotime correlation \n"
-	         "		-s) only twotime correlation + stress tensor   [not available in the B200 build]\n"
+	         "		-s) only twotime correlation + stress tensor \n"
 	         "		-V) velocity correlation \n"
-	         "		-M) magnet correlation                          [not available in the B200 build]\n"
+	         "		-M) magnet correlation \n"
 	         "		-d) Get Amount of dynamic memory allocation \n"
 	         "   -i) argment filename for input variable \n"
 	         "   -g) number of GPUs of this box to shard the particles over   [B200 build only; default 1 or $SQT_GPUS]\n",
@@ -75,9 +78,13 @@ int main(int argc, char **argv)
 			break;
 		case 'V': puts("flag_velocity on : velocity correlation on"); flag_V = true; break; /* lmp2sqt.c:171-173 */
 		case 'g': n_gpus = atoi(optarg); break;
-		case 's': case 'M':
-			fprintf(stderr, "option -%c (stress / magnet correlators) is outside the B200 hot path; use the reference build for it\n", opt);
-			return EXIT_FAILURE;
+		case 's': /* lmp2sqt.c:156-160 */
+			puts("flag_s on : stress tensor calculation on");
+			puts("require flag_t : also on");
+			flag_t = true;
+			flag_s = true;
+			break;
+		case 'M': puts("flag_magnet on : magnet correlation on"); flag_M = true; break; /* :177-179 */
 		default: puts(help_message); return EXIT_FAILURE;
 		}
 	}
@@ -93,10 +100,10 @@ int main(int argc, char **argv)
 	int limitCorrAv = deck.limitCorrAv; /* NB: the reference zeroes the global first (:125) and GetNameList then loads the deck value */
 	if (n_gpus < 1) n_gpus = 1;
 	{ /* before anything is counted or the deck rewritten: what the kernels cannot serve is refused here, with a message */
-		const int max_s = flag_V ? SQT_MAX_NCSPATIAL_V : SQT_MAX_NCSPATIAL;
+		const int max_s = (flag_V || flag_M) ? SQT_MAX_NCSPATIAL_V : SQT_MAX_NCSPATIAL;
 		if (deck.nCSpatial > max_s) {
 			fprintf(stderr, "nCSpatial %d is beyond what the B200 kernels cover (%d%s); use the reference build for this deck\n",
-			        deck.nCSpatial, max_s, flag_V ? " with -V" : "");
+			        deck.nCSpatial, max_s, (flag_V || flag_M) ? " with -V / -M" : "");
 			exit(1);
 		}
 	}
@@ -139,7 +146,9 @@ int main(int argc, char **argv)
 	prm.kVal = deck.kVal; prm.deltaT = deck.deltaT; prm.mass = deck.mass; prm.rVal = deck.rVal;
 	prm.limitCorrAv = limitCorrAv; prm.nCBuffer = deck.nCBuffer; prm.nCSpatial = deck.nCSpatial; prm.nCTime = deck.nCTime;
 	prm.nCSkip = deck.nCSkip; prm.flag_f = flag_f; prm.flag_F = flag_F; prm.flag_t = flag_t; prm.device = device;
-	prm.n_gpus = n_gpus; prm.flag_V = flag_V;
+	prm.n_gpus = n_gpus; prm.flag_V = flag_V; prm.flag_M = flag_M; prm.flag_s = flag_s;
+	const sqt_flags fl = { flag_f, flag_F, flag_t, flag_V, flag_M, flag_s };
+	const bool want_v = flag_V || flag_s, want_m = flag_M;
 	if (deck.nCBuffer > deck.nCTime) { fputs("Error nCBuffer> nCTime\n", stderr); exit(1); }
 
 	if (flag_d) { /* AmountAllocArray, lmp2sqt.c:1658-1820: report and stop */
@@ -200,19 +209,24 @@ int main(int argc, char **argv)
 			double *stage = sqt_multi_stage_acquire(h, hd.n_atoms);
 			if (!stage) die_engine(h, "sqt_stage_acquire", -1);
 			const size_t na = (size_t)hd.n_atoms;
-			if (flag_V && hd.style != 1) {
+			if (want_v && !want_m && hd.style != 1) {
 				/* the reference correlates whatever malloc left in Atom.vx for such dumps (snapshot.c:426-437) */
-				fprintf(stderr, "-V needs dumps written as `id type xu yu zu vx vy vz` (file %s)\n", argv[a]);
+				fprintf(stderr, "-V / -s need dumps written as `id type xu yu zu vx vy vz` (file %s)\n", argv[a]);
 				exit(1);
 			}
-			if (!sqt_reader_read_atoms_v(rd, &hd, stage, stage + na, stage + 2 * na, flag_V ? stage + 3 * na : NULL,
-			                             flag_V ? stage + 4 * na : NULL, flag_V ? stage + 5 * na : NULL)) break;
+			if (want_m && (want_v ? hd.style != 3 : (hd.style != 2 && hd.style != 3))) {
+				fprintf(stderr, "-M needs dumps written as `id type xu yu zu mux muy muz%s` (file %s)\n", want_v ? " vx vy vz" : "", argv[a]);
+				exit(1);
+			}
+			double *sv = want_v ? stage + 3 * na : NULL, *sm = want_m ? stage + (want_v ? 6 : 3) * na : NULL;
+			if (!sqt_reader_read_atoms_vm(rd, &hd, stage, stage + na, stage + 2 * na, sv, sv ? sv + na : NULL, sv ? sv + 2 * na : NULL,
+			                              sm, sm ? sm + na : NULL, sm ? sm + 2 * na : NULL)) break;
 			rc = sqt_multi_push_frame(h, stage, hd.n_atoms, hd.xlo, hd.xhi); /* EvalSpacetimeCorr, :300 */
 			if (rc < 0) die_engine(h, "sqt_push_frame", rc);
 			if (rc == SQT_FLUSH) { /* PrintProcess from AccumSpacetimeCorr, :438-440 */
 				rc = sqt_multi_fetch_results(h, &res);
 				if (rc) die_engine(h, "sqt_fetch_results", rc);
-				if (sqt_host_print_process_v(NULL, &res, &deck, flag_f, flag_F, flag_t, flag_V, NULL)) { perror("PrintProcess"); exit(1); }
+				if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
 			}
 			full_n_snaps_index++;
 			int new_progress = (int)(10000.0 * full_n_snaps_index / full_n_snaps);
@@ -229,7 +243,7 @@ int main(int argc, char **argv)
 	if (rc < 0) die_engine(h, "sqt_finish", rc);
 	if (rc == 1) { /* lmp2sqt.c:327-333 */
 		fprintf(stderr, "limit corr  = %d, countCorrAv = %d\n", limitCorrAv, res.countCorrAv);
-		if (sqt_host_print_process_v(NULL, &res, &deck, flag_f, flag_F, flag_t, flag_V, NULL)) { perror("PrintProcess"); exit(1); }
+		if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
 	}
 	fprintf(stderr, "engine: %d GPU%s; %s; %lld kernel launches\n", sqt_multi_n_gpus(h), sqt_multi_n_gpus(h) > 1 ? "s, particle-sharded" : "",
 	        sqt_kernel_config(sqt_multi_handle(h, 0)), sqt_multi_kernel_launches(h));

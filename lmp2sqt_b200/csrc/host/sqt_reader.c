@@ -14,6 +14,7 @@
 #include "../../../include/sqt_host.h"
 
 #include <fcntl.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
@@ -275,7 +276,7 @@ static inline const char *fast_real(const char *p, const char *lim, double *out)
 	return p;
 }
 
-static inline const char *fast_line(const char *p, const int extra, double *x, double *y, double *z, double *v3)
+static inline const char *fast_line(const char *p, const int extra, double *x, double *y, double *z, double *v3, const int nv)
 {
 	const char *lim = p + FAST_SCAN;
 #define SKIP_SPACES while (*p == ' ' && p < lim) p++
@@ -302,9 +303,9 @@ static inline const char *fast_line(const char *p, const int extra, double *x, d
 		const char *nl = (const char *)memchr(p, '\n', 128); /* trailing blanks or \r */
 		return nl ? nl + 1 : NULL;
 	}
-	if (v3) { /* -V: the three columns after zu are vx vy vz (8-column style only, snapshot.c:285-300) */
+	if (v3) { /* the nv (3 or 6) columns after zu are wanted: vx vy vz (snapshot.c:285-300), mux muy muz (:263-282), or both */
 		const char *q = p;
-		for (int k = 0; k < 3; k++) {
+		for (int k = 0; k < nv; k++) {
 			if (*q != ' ') return NULL;
 			while (*q == ' ' && q < lim) q++;
 			if (!(q = fast_real(q, lim, &v3[k]))) return NULL;
@@ -536,11 +537,23 @@ int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, 
 
 int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz)
 {
+	return sqt_reader_read_atoms_vm(r, hd, x, y, z, vx, vy, vz, NULL, NULL, NULL);
+}
+
+int sqt_reader_read_atoms_vm(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz,
+                             double *mux, double *muy, double *muz)
+{
 	const int n = hd->n_atoms;
 	if (n <= 0) return 1;
-	/* velocities exist only in the 8-column style: the reference's test for the 11-column header is shadowed by its
-	 * 8-column dipole prefix test (snapshot.c:262-283), and the raw frame file carries coordinates only */
-	if (vx && (hd->style != 1 || r->raw == 1)) { r->pos = r->size; return 0; }
+	/* velocities: the 8-column `... vx vy vz` style.  The reference's test for the 11-column header is shadowed by its
+	 * 8-column dipole prefix test (snapshot.c:262-283), so there it never reads the velocities of such a dump; here the
+	 * 11-column style yields them too when BOTH mu and v are asked for (an extension: the reference's -V -M / -s -M runs on
+	 * files correlate uninitialised memory).  The raw frame file carries coordinates only. */
+	if (vx && !((hd->style == 1 && !mux) || (hd->style == 3 && mux)) ) { r->pos = r->size; return 0; }
+	if (vx && r->raw == 1) { r->pos = r->size; return 0; }
+	/* dipoles: the `... mux muy muz [vx vy vz]` styles of a text dump */
+	if (mux && (r->raw != 0 || (hd->style != 2 && hd->style != 3))) { r->pos = r->size; return 0; }
+	const int nv = (vx ? 3 : 0) + (mux ? 3 : 0);
 	if (r->raw == 2) return lb_walk_atoms(r, hd, x, y, z, vx, vy, vz);
 	if (r->raw) { /* already SoA: three straight copies into the staging buffer */
 		const char *src = r->base + r->pos;
@@ -563,7 +576,7 @@ int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x
 	if (r->blk_cursor < r->n_blk && r->blk[r->blk_cursor].atoms_pos == r->pos && r->blk[r->blk_cursor].n_atoms == n) bi = &r->blk[r->blk_cursor];
 	if (bi) endp = bi->end_pos;
 	else if (!index_lines(r, n, step, starts, T, &endp)) { r->pos = r->size; return 0; }
-	const int extra = hd->style ? 3 : 0; /* also for the 11-column style: the reference's 8-column prefix test matches it first (snapshot.c:262) */
+	const int extra = (hd->style == 3 && vx) ? 6 : (hd->style ? 3 : 0); /* 3 also for the 11-column style: the reference's 8-column prefix test matches it first (snapshot.c:262) */
 	int bad = 0;
 #ifdef _OPENMP
 #pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : bad) if (T > 1)
@@ -581,10 +594,11 @@ int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x
 		} else pos = starts[t];
 		for (int i = i0; i < i1; i++) {
 			if (r->size - pos > FAST_MARGIN) { /* far enough from the end of the mapping for the unchecked scan */
-				double v3[3];
-				const char *nx = fast_line(r->base + pos, extra, &x[i], &y[i], &z[i], vx ? v3 : NULL);
+				double v3[6];
+				const char *nx = fast_line(r->base + pos, extra, &x[i], &y[i], &z[i], nv ? v3 : NULL, nv);
 				if (nx) {
-					if (vx) { vx[i] = v3[0]; vy[i] = v3[1]; vz[i] = v3[2]; }
+					if (mux) { mux[i] = v3[0]; muy[i] = v3[1]; muz[i] = v3[2]; }
+					if (vx) { const double *q = v3 + (mux ? 3 : 0); vx[i] = q[0]; vy[i] = q[1]; vz[i] = q[2]; }
 					pos = (size_t)(nx - r->base);
 					continue;
 				}
@@ -597,17 +611,29 @@ int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x
 			x[i] = tok_real(&c, e, &ok);
 			y[i] = tok_real(&c, e, &ok);
 			z[i] = tok_real(&c, e, &ok);
+			if (mux) {
+				mux[i] = tok_real(&c, e, &ok);
+				muy[i] = tok_real(&c, e, &ok);
+				muz[i] = tok_real(&c, e, &ok);
+			}
 			if (vx) {
 				vx[i] = tok_real(&c, e, &ok);
 				vy[i] = tok_real(&c, e, &ok);
 				vz[i] = tok_real(&c, e, &ok);
-			} else
+			}
+			if (!nv)
 				for (int k = extra; k > 0; k--)
 					if (!tok_skip(&c, e)) ok = 0;          /* unused columns of the wider styles must be there too */
 			if (!ok && i != n - 1) bad |= 1; /* a short line fails the frame unless it is the last (snapshot.c:352-356) */
 		}
 	}
 	r->pos = endp;
+	if (mux && !bad) /* make_atom_dipole, snapshot.c:440-459: the reference keeps the unit vector (and leaves the field unset below 1e-3: 0 here) */
+		for (int i = 0; i < n; i++) {
+			const double mu1 = sqrt(mux[i] * mux[i] + muy[i] * muy[i] + muz[i] * muz[i]);
+			if (mu1 > 0.001) { mux[i] = mux[i] / mu1; muy[i] = muy[i] / mu1; muz[i] = muz[i] / mu1; }
+			else mux[i] = muy[i] = muz[i] = 0.0;
+		}
 	return bad ? 0 : 1;
 }
 

@@ -9,7 +9,7 @@
  *
  * Documented deviations (SURVEY.md section 7 "hard parts"):
  *   - Dt columns msdx/msdy/msdz: the reference prints rrMSR1_R_Av, which is uninitialised memory
- *     unless -s is given (lmp2sqt.c:427-431, 532-533); we print 0.
+ *     unless -s is given (lmp2sqt.c:427-431, 532-533); we print 0 then, and the per-axis MSD with -s.
  *   - 1/(N*N) uses a double product; the reference's int product overflows for N > 46340.
  */
 #include "../../../include/sqt_host.h"
@@ -47,6 +47,13 @@ void sqt_host_normalise(sqt_results *r, const sqt_deck *d, int flag_f, int flag_
 
 void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V)
 {
+	const sqt_flags fl = { flag_f, flag_F, flag_t, flag_V, 0, 0 };
+	sqt_host_normalise_x(r, d, &fl);
+}
+
+void sqt_host_normalise_x(sqt_results *r, const sqt_deck *d, const sqt_flags *fl)
+{
+	const int flag_f = fl->f || fl->F, flag_F = fl->F, flag_t = fl->t || fl->s, flag_V = fl->V, flag_M = fl->M, flag_s = fl->s;
 	const int S = r->nCSpatial, T = r->nCTime;
 	const double N = (double)r->nPtls;
 	const double inverseNptls = 1. / N;
@@ -67,6 +74,16 @@ void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int fla
 			for (int q = 0; q < 3; q++)
 				for (int e = 0; e < S * T; e++) c2[q][e] *= inverseNptls * average_number;
 		}
+		if (flag_V && flag_M) { /* :614-617 */
+			double *c2[2] = { r->avC2_mu_v, r->avC2_v_mu };
+			for (int q = 0; q < 2; q++)
+				for (int e = 0; e < S * T; e++) c2[q][e] *= inverseNptls * average_number;
+		}
+		if (flag_M) { /* :618-622 */
+			double *c2[3] = { r->avC2_mu_rho, r->avC2_rho_mu, r->avC2_mu_mu };
+			for (int q = 0; q < 3; q++)
+				for (int e = 0; e < S * T; e++) c2[q][e] *= inverseNptls * average_number;
+		}
 		/* The table is only ever filled under -t (EvalTwoTimeEach as a whole is `if (flag_t)`, lmp2sqt.c:1370): the engine
 		 * leaves it zero otherwise, and scaling zeros is what the reference does then (:625-630) */
 		double *factorDr = (double *)malloc(sizeof(double) * S);
@@ -80,6 +97,7 @@ void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int fla
 		const double factor_msdcm = 1. / (r->countCorrAv);
 		const double factor_Cvv = 1. / (N * r->countCorrAv * 3.);      /* lmp2sqt.c:642-644 */
 		const double factor_Cvcmvcm = 1. / (r->countCorrAv * 3.);
+		const double scale_4stress = .5 * d->mass * d->mass / (r->countCorrAv * r->g_Vol); /* :637 */
 		for (int nt = 0; nt < T; nt++) {
 			r->rrMSDAv[nt] *= scale_factor;
 			r->rrMSDCMAv[nt] *= factor_msdcm;
@@ -87,6 +105,10 @@ void sqt_host_normalise_v(sqt_results *r, const sqt_deck *d, int flag_f, int fla
 			if (flag_V) {
 				r->rrCvvAv[nt] *= factor_Cvv;
 				r->rrCvcmvcmAv[nt] *= factor_Cvcmvcm;
+			}
+			if (flag_s) { /* :660-665; the diagonal / off-diagonal averages (:666-669) are formed by the writer */
+				for (int j = 0; j < 3; j++) r->rrMSR1_R_Av[3 * nt + j] = scale_factor * r->rrMSR1_R_Av[3 * nt + j];
+				for (int j = 0; j < 9; j++) r->rrMSR2_VR_Av[9 * nt + j] = scale_4stress * r->rrMSR2_VR_Av[9 * nt + j];
 			}
 		}
 	}
@@ -151,27 +173,31 @@ static void write_binary(FILE *fp, const sqt_results *r, const sqt_deck *d, int 
 	}
 }
 
-/* PrintEtc, lmp2sqt.c:865-1093 (SSF and Dt; the C2_* and Stress files belong to -V/-M/-s) */
-static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, int flag_f, int flag_t, int flag_V, const char *date)
+/* PrintEtc, lmp2sqt.c:865-1093: SSF, Dt, the C2_* files of -V / -M and the Stress file of -s */
+static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, const sqt_flags *fl, const char *date)
 {
+	const int flag_f = fl->f || fl->F, flag_t = fl->t || fl->s, flag_V = fl->V, flag_M = fl->M, flag_s = fl->s;
 	const int S = r->nCSpatial, T = r->nCTime;
-	char name[64], fn_Dt[512], fn_SSF[512], fn_C2[3][512];
-	static const char *c2_name[3] = { "C2_v_rho", "C2_rho_v", "C2_v_v" };
+	char name[64], fn_Dt[512], fn_SSF[512], fn_stress[512], fn_C2[8][512];
+	static const char *c2_name[8] = { "C2_v_rho", "C2_rho_v", "C2_v_v", "C2_v_mu", "C2_mu_v", "C2_mu_rho", "C2_rho_mu", "C2_mu_mu" };
 	int nfile = 0;
 	do { /* first unused index, probed on the Dt name only (lmp2sqt.c:886-902) */
 		snprintf(name, sizeof(name), "Dt%03d.info.%s", nfile, date);
 		join(fn_Dt, sizeof(fn_Dt), dir, name);
 		snprintf(name, sizeof(name), "SSF%03d.info.%s", nfile, date);
 		join(fn_SSF, sizeof(fn_SSF), dir, name);
-		for (int q = 0; q < 3; q++) {
+		snprintf(name, sizeof(name), "Stress%03d.info.%s", nfile, date);
+		join(fn_stress, sizeof(fn_stress), dir, name);
+		for (int q = 0; q < 8; q++) {
 			snprintf(name, sizeof(name), "%s%03d.info.%s", c2_name[q], nfile, date);
 			join(fn_C2[q], sizeof(fn_C2[q]), dir, name);
 		}
 		nfile++;
 	} while (0 == access(fn_Dt, F_OK));
-	if (flag_f && flag_V) { /* lmp2sqt.c:933-993: one row per lag, "%7.3f" time then " %8.4e" per nk */
-		const double *c2[3] = { r->avC2_v_rho, r->avC2_rho_v, r->avC2_v_v };
-		for (int q = 0; q < 3; q++) {
+	if (flag_f && (flag_V || flag_M)) { /* lmp2sqt.c:933-993: one row per lag, "%7.3f" time then " %8.4e" per nk */
+		const double *c2[8] = { r->avC2_v_rho, r->avC2_rho_v, r->avC2_v_v, r->avC2_v_mu, r->avC2_mu_v, r->avC2_mu_rho, r->avC2_rho_mu, r->avC2_mu_mu };
+		for (int q = 0; q < 8; q++) {
+			if (q < 3 ? !flag_V : (q < 5 ? !(flag_V && flag_M) : !flag_M)) continue;
 			FILE *fp = fopen(fn_C2[q], "w");
 			if (!fp) return -1;
 			for (int nt = 0; nt < T; nt++) {
@@ -192,11 +218,26 @@ static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, i
 		}
 		fclose(fp);
 	}
+	if (flag_s) { /* lmp2sqt.c:1006-1026 */
+		FILE *fp = fopen(fn_stress, "w");
+		if (!fp) return -1;
+		fprintf(fp, "#time MSVR_dig MSVR_offdig xy yx zy yz xz zx\n");
+		fprintf(stderr, "print out stress file\n");
+		for (int nt = 0; nt < T; nt++) {
+			const double *m = r->rrMSR2_VR_Av + 9 * nt; /* xx xy xz yx yy yz zx zy zz */
+			const double dig = (m[0] + m[4] + m[8]) / 3.0;                        /* common.c:164-172 */
+			const double offdig = (m[1] + m[2] + m[3] + m[5] + m[6] + m[7]) / 6.0; /* common.c:161-169 */
+			double tVal = nt * d->deltaT * (d->nCSkip + 1);
+			fprintf(fp, "%8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g \n", tVal, dig, offdig, m[1], m[3], m[7], m[5], m[2], m[6]);
+		}
+		fclose(fp);
+	}
 	if (flag_t) {
 		FILE *fp = fopen(fn_Dt, "w");
 		if (!fp) return -1;
 		fprintf(fp, "#time MSD msdx msdy msdz D(t) anotherform MQD");
 		if (flag_V) fprintf(fp, " Cvv Cvcmvcm");
+		if (flag_M) fprintf(fp, " Cmm");
 		fprintf(fp, " MSDCM\n");
 		fprintf(stderr, "print time correlation \n");
 		double *rrDt = (double *)calloc(T > 3 ? T : 3, sizeof(double));
@@ -211,9 +252,11 @@ static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, i
 			double tVal = nt * d->deltaT * (d->nCSkip + 1);
 			double anotherDt = 0;
 			if (nt != 0) anotherDt = msd[nt] / (tVal * DIM * 2);
-			fprintf(fp, "%8.4f %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g", tVal, msd[nt], 0., 0., 0., rrDt[nt], anotherDt,
-			        r->rrMQDAv[nt]);
+			const double *m1 = r->rrMSR1_R_Av + 3 * nt; /* zero unless -s */
+			fprintf(fp, "%8.4f %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g %8.4g", tVal, msd[nt], flag_s ? m1[0] : 0., flag_s ? m1[1] : 0.,
+			        flag_s ? m1[2] : 0., rrDt[nt], anotherDt, r->rrMQDAv[nt]);
 			if (flag_V) fprintf(fp, " %8.4f %8.4g", r->rrCvvAv[nt], r->rrCvcmvcmAv[nt]);
+			if (flag_M) fprintf(fp, " %8.4f", r->rrCmmAv[nt]); /* always 0: the reference never adds to rrCmmAv (lmp2sqt.c:420-432) */
 			fprintf(fp, " %8.4f\n", r->rrMSDCMAv[nt]);
 		}
 		free(rrDt);
@@ -231,6 +274,13 @@ int sqt_host_print_process(const char *dir, sqt_results *r, const sqt_deck *d, i
 int sqt_host_print_process_v(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V,
                              const char *date)
 {
+	const sqt_flags fl = { flag_f, flag_F, flag_t, flag_V, 0, 0 };
+	return sqt_host_print_process_x(dir, r, d, &fl, date);
+}
+
+int sqt_host_print_process_x(const char *dir, sqt_results *r, const sqt_deck *d, const sqt_flags *fl, const char *date)
+{
+	const int flag_f = fl->f || fl->F, flag_F = fl->F;
 	char today[32], path[512];
 	if (!date) {
 		time_t raw = time(NULL);
@@ -241,8 +291,8 @@ int sqt_host_print_process_v(const char *dir, sqt_results *r, const sqt_deck *d,
 	FILE *flog = fopen(path, "w+");
 	if (!flog) return -1;
 	fputs("Call PrintProcess : \n", flog);
-	sqt_host_normalise_v(r, d, flag_f, flag_F, flag_t, flag_V);
-	if (write_etc(dir, r, d, flag_f, flag_t, flag_V, date)) { fclose(flog); return -1; }
+	sqt_host_normalise_x(r, d, fl);
+	if (write_etc(dir, r, d, fl, date)) { fclose(flog); return -1; }
 	if (flag_f) {
 		const char *fout_filename = "output.binary";
 		join(path, sizeof(path), dir, fout_filename);

@@ -24,8 +24,9 @@ struct sqt_handle {
 	int device, n_sm;
 	char err[512];
 	char cfg[1024];
-	bool flag_f, flag_F, flag_t, flag_V;
-	int ncomp;                // arrays per frame: 3 (x y z) or 6 (+ vx vy vz with -V)
+	bool flag_f, flag_F, flag_t, flag_V, flag_M, flag_s;
+	int ncomp;                // arrays per frame: x y z, then vx vy vz (-V or -s), then mux muy muz (-M)
+	int comp_v, comp_m;       // first component of the velocities / dipoles (-1: not carried)
 
 	// ---- ring bookkeeping (host mirror of TBuf.count etc.) ----
 	int limitCorrAv, countCorrAv, n_print;
@@ -54,7 +55,9 @@ struct sqt_handle {
 	int *d_hist_cur, *d_bufHist;
 	double *d_bufFs, *d_bufF, *d_bufMSD, *d_bufMQD, *d_bufMSDCM;
 	double *d_rho0, *d_sumr0, *d_invL0, *d_rho_cur, *d_cblk;
-	int rho_n;                // 6 nCS + 3: one block of d_rho_cur (rho + sum r; with -V a second block kvel + sum v follows)
+	int rho_n;                // 6 nCS + 3: one field block of d_rho_cur (rho + sum r; then kvel + sum v with -V, kmu + sum mu with -M)
+	int n_fields, blk_v, blk_m; // field blocks in use and where kvel / kmu sit; then 9 doubles sum_n v (x) r (-s), then a scratch block
+	int off_vr, off_scratch, coll_n; // offsets into d_rho_cur; doubles the per-frame allreduce covers
 	long long *d_thr;
 	double *d_avblk, *d_latblk; // [10*S*T + 5*T]
 	size_t avblk_n;
@@ -73,6 +76,9 @@ struct sqt_handle {
 	// -V
 	double *d_vring, *d_vpartial, *d_bufC2, *d_bufCvv, *d_bufCvcm, *d_kvel0, *d_sumv0;
 	int vel_nchunk, vel_chunk;
+	// -M, -s
+	double *d_kmu0, *d_sumVR_state, *d_orgSumVR, *d_bufMSR1, *d_bufMSR2, *d_axis_partial, *d_vr_partial;
+	long long vr_frames;      // processed frames so far (parity of the double-buffered sum_n v (x) r state)
 	cudaStream_t s_main, s_copy, s_coll, s_aux;
 	cudaEvent_t ev_red, ev_coll, ev_rho, ev_rhoc, ev_prod, ev_t0, ev_t1;
 	bool coll_pending, rhoc_pending;
@@ -107,11 +113,13 @@ extern "C" int sqt_results_alloc(sqt_results *r, int S, int T)
 	if (!r || S < 1 || T < 1) return SQT_ERR_ARG;
 	memset(r, 0, sizeof(*r));
 	r->nCSpatial = S; r->nCTime = T;
-	double **a2[10] = { &r->avF_qq2, &r->StdDevF_qq2, &r->avF_s_qq2, &r->StdDevF_s_qq2, &r->avF_d_qq2, &r->StdDevF_d_qq2, &r->avDrTable,
-	                    &r->avC2_v_rho, &r->avC2_rho_v, &r->avC2_v_v };
-	double **a1[5] = { &r->rrMSDAv, &r->rrMQDAv, &r->rrMSDCMAv, &r->rrCvvAv, &r->rrCvcmvcmAv };
-	for (int i = 0; i < 10; ++i) if (!(*a2[i] = (double *)calloc((size_t)S * T, sizeof(double)))) return SQT_ERR_NOMEM;
-	for (int i = 0; i < 5; ++i) if (!(*a1[i] = (double *)calloc(T, sizeof(double)))) return SQT_ERR_NOMEM;
+	double **a2[SQT_N2D] = { &r->avF_qq2, &r->StdDevF_qq2, &r->avF_s_qq2, &r->StdDevF_s_qq2, &r->avF_d_qq2, &r->StdDevF_d_qq2, &r->avDrTable,
+	                         &r->avC2_v_rho, &r->avC2_rho_v, &r->avC2_v_v, &r->avC2_v_mu, &r->avC2_mu_v, &r->avC2_mu_rho, &r->avC2_rho_mu, &r->avC2_mu_mu };
+	double **a1[6] = { &r->rrMSDAv, &r->rrMQDAv, &r->rrMSDCMAv, &r->rrCvvAv, &r->rrCvcmvcmAv, &r->rrCmmAv };
+	for (int i = 0; i < SQT_N2D; ++i) if (!(*a2[i] = (double *)calloc((size_t)S * T, sizeof(double)))) return SQT_ERR_NOMEM;
+	for (int i = 0; i < 6; ++i) if (!(*a1[i] = (double *)calloc(T, sizeof(double)))) return SQT_ERR_NOMEM;
+	if (!(r->rrMSR1_R_Av = (double *)calloc((size_t)T * 3, sizeof(double)))) return SQT_ERR_NOMEM;
+	if (!(r->rrMSR2_VR_Av = (double *)calloc((size_t)T * 9, sizeof(double)))) return SQT_ERR_NOMEM;
 	return SQT_OK;
 }
 
@@ -122,6 +130,8 @@ extern "C" void sqt_results_free(sqt_results *r)
 	free(r->avF_d_qq2); free(r->StdDevF_d_qq2); free(r->avDrTable);
 	free(r->rrMSDAv); free(r->rrMQDAv); free(r->rrMSDCMAv);
 	free(r->avC2_v_rho); free(r->avC2_rho_v); free(r->avC2_v_v); free(r->rrCvvAv); free(r->rrCvcmvcmAv);
+	free(r->avC2_v_mu); free(r->avC2_mu_v); free(r->avC2_mu_rho); free(r->avC2_rho_mu); free(r->avC2_mu_mu); free(r->rrCmmAv);
+	free(r->rrMSR1_R_Av); free(r->rrMSR2_VR_Av);
 	memset(r, 0, sizeof(*r));
 }
 
@@ -150,8 +160,8 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	if (p->nCSpatial < 1 || p->nCTime < 1) return fail(h, SQT_ERR_ARG, "sqt_create: nCSpatial and nCTime must be >= 1");
 	if (p->nCSpatial > SQT_MAX_NCSPATIAL)
 		return fail(h, SQT_ERR_ARG, "sqt_create: nCSpatial %d is beyond what the kernels cover (%d)", p->nCSpatial, SQT_MAX_NCSPATIAL);
-	if (p->flag_V && p->nCSpatial > SQT_MAX_NCSPATIAL_V)
-		return fail(h, SQT_ERR_ARG, "sqt_create: -V needs nCSpatial <= %d (got %d)", SQT_MAX_NCSPATIAL_V, p->nCSpatial);
+	if ((p->flag_V || p->flag_M) && p->nCSpatial > SQT_MAX_NCSPATIAL_V)
+		return fail(h, SQT_ERR_ARG, "sqt_create: -V / -M need nCSpatial <= %d (got %d)", SQT_MAX_NCSPATIAL_V, p->nCSpatial);
 	if (!(p->rVal > 0)) return fail(h, SQT_ERR_ARG, "sqt_create: rVal must be > 0");
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -169,9 +179,13 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->device = p->device;
 	h->flag_F = p->flag_F != 0;
 	h->flag_f = p->flag_f != 0 || h->flag_F; // -F switches -f on as well (lmp2sqt.c:160-165)
-	h->flag_t = p->flag_t != 0;
+	h->flag_s = p->flag_s != 0;
+	h->flag_t = p->flag_t != 0 || h->flag_s; // -s switches -t on as well (lmp2sqt.c:156-160)
 	h->flag_V = p->flag_V != 0;
-	h->ncomp = h->flag_V ? 6 : 3;
+	h->flag_M = p->flag_M != 0;
+	h->comp_v = (h->flag_V || h->flag_s) ? 3 : -1;
+	h->comp_m = h->flag_M ? (h->comp_v >= 0 ? 6 : 3) : -1;
+	h->ncomp = 3 + (h->comp_v >= 0 ? 3 : 0) + (h->comp_m >= 0 ? 3 : 0);
 	h->limitCorrAv = p->limitCorrAv;
 	h->countCorrAv = 0; h->n_print = 0; h->nSkip = 0; h->p_file = 0;
 	h->count.assign(h->B, 0);
@@ -188,6 +202,8 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->d_avblk = h->d_latblk = nullptr;
 	h->d_vring = h->d_vpartial = h->d_bufC2 = h->d_bufCvv = h->d_bufCvcm = h->d_kvel0 = h->d_sumv0 = nullptr;
 	h->vel_nchunk = h->vel_chunk = 0;
+	h->d_kmu0 = h->d_sumVR_state = h->d_orgSumVR = h->d_bufMSR1 = h->d_bufMSR2 = h->d_axis_partial = h->d_vr_partial = nullptr;
+	h->vr_frames = 0;
 	h->latched = false; h->latched_count = 0; h->latched_limit = 0;
 	h->comm = nullptr; h->rank = 0; h->nranks = 1; h->launches = 0; h->prof = false; h->prof_used = 0;
 	h->coll_pending = h->rhoc_pending = false;
@@ -240,12 +256,35 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	CUC(cudaMalloc(&h->d_invL0, sizeof(double) * B));
 	CUC(cudaMemset(h->d_invL0, 0, sizeof(double) * B));
 	h->rho_n = 6 * (int)S + 3;
-	CUC(cudaMalloc(&h->d_rho_cur, sizeof(double) * 3 * h->rho_n)); // rho + sum r | kvel + sum v (-V) | scratch
-	CUC(cudaMemset(h->d_rho_cur, 0, sizeof(double) * 3 * h->rho_n));
-	CUC(cudaMalloc(&h->d_cblk, sizeof(double) * (2 * T * S + 3 * T)));
+	h->blk_v = h->flag_V ? 1 : -1;
+	h->blk_m = h->flag_M ? (h->flag_V ? 2 : 1) : -1;
+	h->n_fields = 1 + (h->flag_V ? 1 : 0) + (h->flag_M ? 1 : 0);
+	h->off_vr = h->n_fields * h->rho_n;
+	h->coll_n = h->off_vr + (h->flag_s ? 9 : 0);
+	h->off_scratch = h->off_vr + 16;
+	CUC(cudaMalloc(&h->d_rho_cur, sizeof(double) * (h->off_scratch + h->rho_n))); // rho + sum r | kvel + sum v (-V) | kmu + sum mu (-M) | sum v (x) r (-s) | scratch
+	CUC(cudaMemset(h->d_rho_cur, 0, sizeof(double) * (h->off_scratch + h->rho_n)));
+	CUC(cudaMalloc(&h->d_cblk, sizeof(double) * (2 * T * S + 6 * T)));
+	CUC(cudaMemset(h->d_cblk, 0, sizeof(double) * (2 * T * S + 6 * T)));
+	if (h->flag_M) {
+		CUC(cudaMalloc(&h->d_kmu0, sizeof(double) * B * 6 * S));
+		CUC(cudaMemset(h->d_kmu0, 0, sizeof(double) * B * 6 * S));
+	}
+	if (h->flag_s) {
+		CUC(cudaMalloc(&h->d_sumVR_state, sizeof(double) * 18));
+		CUC(cudaMemset(h->d_sumVR_state, 0, sizeof(double) * 18));
+		CUC(cudaMalloc(&h->d_orgSumVR, sizeof(double) * B * 9));
+		CUC(cudaMemset(h->d_orgSumVR, 0, sizeof(double) * B * 9));
+		CUC(cudaMalloc(&h->d_bufMSR1, sizeof(double) * B * T * 3));
+		CUC(cudaMemset(h->d_bufMSR1, 0, sizeof(double) * B * T * 3));
+		CUC(cudaMalloc(&h->d_bufMSR2, sizeof(double) * B * T * 9));
+		CUC(cudaMemset(h->d_bufMSR2, 0, sizeof(double) * B * T * 9));
+	}
+	if (h->flag_V || h->flag_M) {
+		CUC(cudaMalloc(&h->d_bufC2, sizeof(double) * SQT_NC2 * B * T * S));
+		CUC(cudaMemset(h->d_bufC2, 0, sizeof(double) * SQT_NC2 * B * T * S));
+	}
 	if (h->flag_V) {
-		CUC(cudaMalloc(&h->d_bufC2, sizeof(double) * 3 * B * T * S));
-		CUC(cudaMemset(h->d_bufC2, 0, sizeof(double) * 3 * B * T * S));
 		double **vb[] = { &h->d_bufCvv, &h->d_bufCvcm };
 		for (auto pp : vb) { CUC(cudaMalloc(pp, sizeof(double) * B * T)); CUC(cudaMemset(*pp, 0, sizeof(double) * B * T)); }
 		CUC(cudaMalloc(&h->d_kvel0, sizeof(double) * B * 6 * S));
@@ -253,7 +292,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 		CUC(cudaMalloc(&h->d_sumv0, sizeof(double) * B * 3));
 		CUC(cudaMemset(h->d_sumv0, 0, sizeof(double) * B * 3));
 	}
-	h->avblk_n = 10 * S * T + 5 * T;
+	h->avblk_n = SQT_N2D * S * T + SQT_N1D * T;
 	CUC(cudaMalloc(&h->d_avblk, sizeof(double) * h->avblk_n));
 	CUC(cudaMemset(h->d_avblk, 0, sizeof(double) * h->avblk_n)); // ZeroAvSpacetimeCorr, lmp2sqt.c:1921
 	CUC(cudaMalloc(&h->d_latblk, sizeof(double) * h->avblk_n));
@@ -275,6 +314,8 @@ static void release_sized(sqt_handle *h)
 	for (int i = 0; i < 2; ++i) { cudaFree(h->d_cur[i]); h->d_cur[i] = nullptr; }
 	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr);
 	cudaFree(h->d_rho_partial); cudaFree(h->d_mma_extra); cudaFree(h->d_rho_extra); cudaFree(h->d_vring); cudaFree(h->d_vpartial);
+	cudaFree(h->d_axis_partial); cudaFree(h->d_vr_partial);
+	h->d_axis_partial = h->d_vr_partial = nullptr;
 	h->d_ring = h->d_partial = h->d_mma_partial = h->d_rho_partial = h->d_mma_extra = h->d_rho_extra = h->d_vring = h->d_vpartial = nullptr;
 	h->d_tile_ctr = h->d_mma_ctr = nullptr;
 	h->sized = false;
@@ -297,6 +338,7 @@ extern "C" void sqt_destroy(sqt_handle *h)
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
 	cudaFree(h->d_bufC2); cudaFree(h->d_bufCvv); cudaFree(h->d_bufCvcm); cudaFree(h->d_kvel0); cudaFree(h->d_sumv0);
+	cudaFree(h->d_kmu0); cudaFree(h->d_sumVR_state); cudaFree(h->d_orgSumVR); cudaFree(h->d_bufMSR1); cudaFree(h->d_bufMSR2);
 	for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
 	cudaEvent_t evs[] = { h->ev_red, h->ev_coll, h->ev_rho, h->ev_rhoc, h->ev_prod, h->ev_t0, h->ev_t1 };
 	for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -369,7 +411,7 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 	h->vc.on = 0;
 	if (want_self && !h->mc.on && h->mc.geo) { // (rho(k) comes from the tensor-core rho kernel on this path)
 		// without a communicator (and without -V) the whole frame is two launches: rho(k) rides in the vector kernel
-		const int fuse = !h->comm && !h->flag_V && h->flag_F;
+		const int fuse = !h->comm && !h->flag_V && !h->flag_M && !h->flag_s && h->flag_F;
 		rc = sqt_pick_vec(h->S, h->flag_F ? h->S : 1, h->B, n_local, h->n_sm, fuse, &h->vc);
 		if (rc != 0) return fail(h, SQT_ERR_CUDA, "vector kernel selection failed (rc=%d)", rc);
 	}
@@ -409,7 +451,7 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
 	}
 	h->rmc.on = 0;
-	if ((h->self_kind != SELF_CLASSIC || h->flag_V) && !h->fused) {
+	if ((h->self_kind != SELF_CLASSIC || h->flag_V || h->flag_M) && !h->fused) {
 		const char *rm = getenv("SQT_RHO_MMA");
 		if (!(rm && *rm == '0')) {
 			rc = sqt_pick_rho_mma(h->mc, n_local, h->n_sm, &h->rmc);
@@ -422,8 +464,16 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 			mma_bytes += rb;
 		}
 	}
+	if ((h->flag_V || h->flag_M) && !h->rmc.on)
+		return fail(h, SQT_ERR_ARG, "-V / -M need the tensor-core rho(k) kernel (nCSpatial <= %d, SQT_MMA / SQT_RHO_MMA not 0)", SQT_MAX_NCSPATIAL_V);
+	if (h->flag_s) {
+		int chunk = 8192, nch = (n_local + chunk - 1) / chunk;
+		if (nch > 2048) { nch = 2048; chunk = (n_local + nch - 1) / nch; nch = (n_local + chunk - 1) / chunk; }
+		h->vel_chunk = chunk; h->vel_nchunk = nch;
+		CU(cudaMalloc(&h->d_axis_partial, sizeof(double) * 3 * (size_t)h->B * nch));
+		CU(cudaMalloc(&h->d_vr_partial, sizeof(double) * 9 * 1024));
+	}
 	if (h->flag_V) {
-		if (!h->rmc.on) return fail(h, SQT_ERR_ARG, "-V needs the tensor-core rho(k) kernel (nCSpatial <= %d, SQT_MMA / SQT_RHO_MMA not 0)", SQT_MAX_NCSPATIAL_V);
 		if (h->flag_t) {
 			const size_t vb = sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np;
 			cudaError_t e = cudaMalloc(&h->d_vring, vb);
@@ -462,7 +512,9 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		off = snprintf(h->cfg, sizeof(h->cfg), "%s%s", classic, h->rmc.on ? "; + rho(k), kvel: " : "");
 	if (h->rmc.on)
 		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "rho_mma_kernel<NT=%d> grid=%d block=%d smem=%zuB occ=%d blocks/SM, static tiles of 32 particles%s",
-		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ, h->flag_V ? " (+ velocity-weighted pass, vel_ring_kernel)" : "");
+		                h->mc.NT, h->rmc.blocks, h->rmc.WPB * 32, h->rmc.smem, h->rmc.occ,
+		                h->flag_V && h->flag_M ? " (+ velocity- and dipole-weighted passes, vel_ring_kernel)"
+		                : h->flag_V ? " (+ velocity-weighted pass, vel_ring_kernel)" : h->flag_M ? " (+ dipole-weighted pass)" : "");
 	if (h->self_kind != SELF_CLASSIC)
 		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "%s%s", h->rmc.on ? "; unused: " : "", classic);
 	snprintf(h->cfg + off, sizeof(h->cfg) - off, "; slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB", h->B, SQT_NVIRT, ring_bytes / 1e9,
@@ -501,13 +553,17 @@ static int stage_collective(sqt_handle *h, int p, long long n_total, bool split)
 		CU(cudaEventRecord(h->ev_rho, h->s_main));
 		CU(cudaStreamWaitEvent(h->s_coll, h->ev_rho, 0));
 	}
-	if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_rho_cur, (size_t)h->rho_n * (h->flag_V ? 2 : 1), h->s_coll, h->err, sizeof(h->err)))
+	if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_rho_cur, (size_t)h->coll_n, h->s_coll, h->err, sizeof(h->err)))
 		return SQT_ERR_NCCL;
 	CollectiveArgs ca;
 	ca.rho_cur = h->d_rho_cur; ca.rho0 = h->d_rho0; ca.sumr0 = h->d_sumr0; ca.bufF = h->d_bufF; ca.bufMSDCM = h->d_bufMSDCM;
 	ca.p = p; ca.T = T; ca.B = B; ca.nCS = S;
 	ca.inv_n2 = 1.0 / ((double)n_total * (double)n_total);
 	ca.flag_V = h->flag_V; ca.kvel0 = h->d_kvel0; ca.sumv0 = h->d_sumv0; ca.bufC2 = h->d_bufC2; ca.bufCvcm = h->d_bufCvcm;
+	ca.flag_M = h->flag_M; ca.kmu0 = h->d_kmu0; ca.rho_n = h->rho_n; ca.blk_v = h->blk_v; ca.blk_m = h->blk_m;
+	ca.flag_s = h->flag_s; ca.off_vr = h->off_vr; ca.vr_cumulative = !h->flag_f; ca.vr_parity = (int)(h->vr_frames & 1);
+	ca.sumVR_state = h->d_sumVR_state; ca.orgSumVR = h->d_orgSumVR; ca.bufMSR2 = h->d_bufMSR2;
+	h->vr_frames++;
 	int rc = sqt_launch_collective(ca, h->s_coll);
 	if (rc) return fail(h, SQT_ERR_CUDA, "collective_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 	h->launches++;
@@ -530,13 +586,13 @@ static int accumulate_completed(sqt_handle *h, int done_on_device, int *status)
 			aa.nb = nb; aa.T = T; aa.nCS = S; aa.B = B;
 			aa.bufF = h->d_bufF; aa.bufFs = h->d_bufFs; aa.bufMSD = h->d_bufMSD; aa.bufMQD = h->d_bufMQD; aa.bufMSDCM = h->d_bufMSDCM;
 			aa.bufHist = h->d_bufHist; aa.cblk = h->d_cblk;
-			aa.flag_f = h->flag_f; aa.flag_F = h->flag_F; aa.flag_t = h->flag_t; aa.flag_V = h->flag_V;
-			aa.bufC2 = h->d_bufC2; aa.bufCvv = h->d_bufCvv; aa.bufCvcm = h->d_bufCvcm;
-			for (int i = 0; i < 10; ++i) aa.av[i] = h->d_avblk + (size_t)i * ST;
-			for (int i = 0; i < 5; ++i) aa.av1[i] = h->d_avblk + 10 * ST + (size_t)i * T;
+			aa.flag_f = h->flag_f; aa.flag_F = h->flag_F; aa.flag_t = h->flag_t; aa.flag_V = h->flag_V; aa.flag_M = h->flag_M; aa.flag_s = h->flag_s;
+			aa.bufC2 = h->d_bufC2; aa.bufCvv = h->d_bufCvv; aa.bufCvcm = h->d_bufCvcm; aa.bufMSR1 = h->d_bufMSR1; aa.bufMSR2 = h->d_bufMSR2;
+			for (int i = 0; i < SQT_N2D; ++i) aa.av[i] = h->d_avblk + (size_t)i * ST;
+			for (int i = 0; i < SQT_N1D; ++i) aa.av1[i] = h->d_avblk + SQT_N2D * ST + (size_t)i * T;
 			rc = sqt_launch_pack(aa, h->s_coll);
 			if (rc) return fail(h, SQT_ERR_CUDA, "buffer_pack_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-			if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * ST + 3 * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
+			if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * ST + (h->flag_s ? 6 : 3) * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
 				return SQT_ERR_NCCL;
 			rc = sqt_launch_accumulate(aa, h->s_coll);
 			if (rc) return fail(h, SQT_ERR_CUDA, "buffer_accumulate_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -557,6 +613,19 @@ static int accumulate_completed(sqt_handle *h, int done_on_device, int *status)
 			*status = SQT_FLUSH;
 		}
 	}
+	return SQT_OK;
+}
+
+// -s: this shard's sum_n v (x) r of the frame into d_rho_cur + off_vr (EvalOneTimeSumVR, lmp2sqt.c:1122-1142)
+static int launch_sum_vr(sqt_handle *h, const double *cur, long long cur_pitch)
+{
+	SumVRArgs sa;
+	sa.cur = cur; sa.partial = h->d_vr_partial; sa.out = h->d_rho_cur + h->off_vr; sa.cur_pitch = cur_pitch; sa.n_local = h->n_local;
+	sa.nblocks = (h->n_local + 255) / 256;
+	if (sa.nblocks > 1024) sa.nblocks = 1024;
+	const int rc = sqt_launch_sum_vr(sa, h->s_main);
+	if (rc) return fail(h, SQT_ERR_CUDA, "sum_vr_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+	h->launches += 2;
 	return SQT_OK;
 }
 
@@ -611,7 +680,7 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		fa.flag_f = h->flag_f; fa.flag_F = h->flag_F; fa.flag_t = h->flag_t;
 		const size_t ST = (size_t)S * T;
 		for (int i = 0; i < 7; ++i) fa.av[i] = h->d_avblk + (size_t)i * ST;
-		for (int i = 0; i < 3; ++i) fa.av1[i] = h->d_avblk + 10 * ST + (size_t)i * T;
+		for (int i = 0; i < 3; ++i) fa.av1[i] = h->d_avblk + SQT_N2D * ST + (size_t)i * T;
 		rc = sqt_launch_vec_finish(fa, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "vec_finish_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches += 2;
@@ -640,13 +709,23 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches += 2;
 		if (h->flag_V) { // kvel_q1 (lmp2sqt.c:1203-1208): the same pass with the velocity component as the particle's weight
-			qa.wt = cur + 3 * cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + h->rho_n;
+			qa.wt = cur + h->comp_v * cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + (size_t)h->blk_v * h->rho_n;
 			rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
 			if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel (velocity-weighted) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 			h->launches += 2;
 		}
+		if (h->flag_M) { // kmu_q1 (:1209-1214): and with the dipole component
+			qa.wt = cur + h->comp_m * cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + (size_t)h->blk_m * h->rho_n;
+			rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
+			if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel (dipole-weighted) launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+			h->launches += 2;
+		}
 		if (h->prof) CU(cudaEventRecord(pe1, h->s_main));
-		if (h->self_kind != SELF_CLASSIC) { rc = stage_collective(h, p, n_total, split); if (rc) return rc; }
+		if (h->self_kind != SELF_CLASSIC) {
+			if (h->flag_s) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
+			rc = stage_collective(h, p, n_total, split);
+			if (rc) return rc;
+		}
 	}
 
 	// ---- stage B: the per-particle terms over the origin ring ---------------------------------------------------------
@@ -686,11 +765,21 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
 	if (h->d_vring) { // -V -t: rrCvv over the origin-velocity ring (lmp2sqt.c:1397-1401, 1441)
 		VelArgs va;
-		va.vcur = cur + 3 * cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
+		va.vcur = cur + h->comp_v * cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
 		va.cur_pitch = cur_pitch; va.RP = h->ring_np; va.n_local = h->n_local; va.nchunk = h->vel_nchunk; va.chunk = h->vel_chunk;
 		va.p = p; va.T = T; va.B = B;
 		rc = sqt_launch_vel(va, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "vel_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches += 2;
+	}
+	if (h->flag_s) { // -s: rrMSR1_R, the per-axis squares of the displacements (lmp2sqt.c:1434-1436): one more pass over the origin ring
+		const bool lane = h->self_kind == SELF_MMA || h->self_kind == SELF_VEC;
+		AxisMsdArgs xa;
+		xa.cur = cur; xa.ring = h->d_ring; xa.partial = h->d_axis_partial; xa.bufMSR1 = h->d_bufMSR1; xa.cur_pitch = cur_pitch;
+		xa.s_slot = lane ? 3 * h->ring_np : 1; xa.s_axis = lane ? h->ring_np : h->RP; xa.s_ptl = lane ? 1 : 3 * (long long)h->RP;
+		xa.n_local = h->n_local; xa.nchunk = h->vel_nchunk; xa.chunk = h->vel_chunk; xa.p = p; xa.T = T; xa.B = B;
+		rc = sqt_launch_axis_msd(xa, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "axis_msd_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches += 2;
 	}
 	CU(cudaEventRecord(h->ev_ring[slot], h->s_main)); // d_cur[slot] may be overwritten by the copy of the frame after next
@@ -713,11 +802,15 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
 		rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.invL0 = h->d_invL0; rr.invL = invL;
 		// with the tensor-core rho kernel on (-V on the recurrence path) rho(k) is already final: the virtual slots' copy goes to scratch
-		rr.rho_cur = h->rmc.on ? h->d_rho_cur + 2 * h->rho_n : h->d_rho_cur;
+		rr.rho_cur = h->rmc.on ? h->d_rho_cur + h->off_scratch : h->d_rho_cur;
 		rc = sqt_launch_reduce(rr, h->s_main);
 		if (rc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 		h->launches++;
-		if (!h->rmc.on || h->self_kind == SELF_CLASSIC) { rc = stage_collective(h, p, n_total, split); if (rc) return rc; }
+		if (!h->rmc.on || h->self_kind == SELF_CLASSIC) {
+			if (h->flag_s) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
+			rc = stage_collective(h, p, n_total, split);
+			if (rc) return rc;
+		}
 	}
 	if (split) {
 		CU(cudaEventRecord(h->ev_red, h->s_main));
@@ -746,7 +839,7 @@ static int push_common(sqt_handle *h, const double *const *comp, bool on_device,
 	if (h->broken) return fail(h, SQT_ERR_STATE, "the handle failed while sizing its arrays for the first frame and cannot take frames");
 	if (!on_device)
 		for (int a = 0; a < h->ncomp; ++a)
-			if (!comp[a]) return fail(h, SQT_ERR_ARG, "push_frame: -V needs the velocity arrays");
+			if (!comp[a]) return fail(h, SQT_ERR_ARG, "push_frame: -V / -s need the velocity arrays and -M the dipole arrays");
 	if (!(xhi > xlo)) return fail(h, SQT_ERR_ARG, "push_frame: box xhi must exceed xlo");
 	if (h->nSkip < h->p.nCSkip) { h->nSkip++; return SQT_OK; } // lmp2sqt.c:1612-1615
 	CU(cudaSetDevice(h->device));
@@ -773,7 +866,7 @@ static int push_common(sqt_handle *h, const double *const *comp, bool on_device,
 		}
 		return rcf;
 	} else {
-		const double *src[6];
+		const double *src[9];
 		for (int a = 0; a < h->ncomp; ++a) src[a] = comp[a];
 		if (comp[0] == h->h_stage[0] && h->stage_cap) slot = 0;
 		else if (comp[0] == h->h_stage[1] && h->stage_cap) slot = 1;
@@ -806,29 +899,39 @@ static int push_common(sqt_handle *h, const double *const *comp, bool on_device,
 extern "C" int sqt_push_frame(sqt_handle *h, const double *soa, int n_local, long long n_total, double xlo, double xhi)
 {
 	if (!h || !soa || n_local < 1) return h ? fail(h, SQT_ERR_ARG, "push_frame: bad arguments") : SQT_ERR_ARG;
-	const double *comp[6];
-	for (int a = 0; a < 6; ++a) comp[a] = a < h->ncomp ? soa + (size_t)a * n_local : nullptr;
+	const double *comp[9];
+	for (int a = 0; a < 9; ++a) comp[a] = a < h->ncomp ? soa + (size_t)a * n_local : nullptr;
 	return push_common(h, comp, false, nullptr, n_local, n_total, xlo, xhi);
 }
 
 extern "C" int sqt_push_frame_xyz(sqt_handle *h, const double *x, const double *y, const double *z, const double *vx, const double *vy,
                                   const double *vz, int n_local, long long n_total, double xlo, double xhi)
 {
-	const double *comp[6] = { x, y, z, vx, vy, vz };
-	if (h && (!y || !z)) return fail(h, SQT_ERR_ARG, "push_frame_xyz: null coordinate array");
+	return sqt_push_frame_xyz_vm(h, x, y, z, vx, vy, vz, nullptr, nullptr, nullptr, n_local, n_total, xlo, xhi);
+}
+
+extern "C" int sqt_push_frame_xyz_vm(sqt_handle *h, const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                                     const double *vz, const double *mux, const double *muy, const double *muz, int n_local, long long n_total,
+                                     double xlo, double xhi)
+{
+	if (!h) return SQT_ERR_ARG;
+	if (!y || !z) return fail(h, SQT_ERR_ARG, "push_frame_xyz: null coordinate array");
+	const double *comp[9] = { x, y, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	if (h->comp_v >= 0) { comp[h->comp_v] = vx; comp[h->comp_v + 1] = vy; comp[h->comp_v + 2] = vz; }
+	if (h->comp_m >= 0) { comp[h->comp_m] = mux; comp[h->comp_m + 1] = muy; comp[h->comp_m + 2] = muz; }
 	return push_common(h, comp, false, nullptr, n_local, n_total, xlo, xhi);
 }
 
 extern "C" int sqt_push_frame_device(sqt_handle *h, const double *d_soa, int n_local, long long n_total, double xlo, double xhi)
 {
-	const double *comp[6] = { d_soa, nullptr, nullptr, nullptr, nullptr, nullptr };
+	const double *comp[9] = { d_soa, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	return push_common(h, comp, true, nullptr, n_local, n_total, xlo, xhi);
 }
 
 extern "C" int sqt_push_frame_device_ex(sqt_handle *h, const double *d_soa, int n_local, long long n_total, double xlo, double xhi,
                                         void *producer_stream)
 {
-	const double *comp[6] = { d_soa, nullptr, nullptr, nullptr, nullptr, nullptr };
+	const double *comp[9] = { d_soa, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	return push_common(h, comp, true, producer_stream, n_local, n_total, xlo, xhi);
 }
 
@@ -850,11 +953,19 @@ static int copy_results(sqt_handle *h, const double *d_blk, sqt_results *out, in
 	int rc = sqt_sync(h);
 	if (rc) return rc;
 	const size_t ST = (size_t)h->S * h->T, T = h->T;
-	double *a2[10] = { out->avF_qq2, out->StdDevF_qq2, out->avF_s_qq2, out->StdDevF_s_qq2, out->avF_d_qq2, out->StdDevF_d_qq2, out->avDrTable,
-	                   out->avC2_v_rho, out->avC2_rho_v, out->avC2_v_v };
-	double *a1[5] = { out->rrMSDAv, out->rrMQDAv, out->rrMSDCMAv, out->rrCvvAv, out->rrCvcmvcmAv };
-	for (int i = 0; i < 10; ++i) if (a2[i]) CU(cudaMemcpy(a2[i], d_blk + i * ST, sizeof(double) * ST, cudaMemcpyDeviceToHost));
-	for (int i = 0; i < 5; ++i) if (a1[i]) CU(cudaMemcpy(a1[i], d_blk + 10 * ST + i * T, sizeof(double) * T, cudaMemcpyDeviceToHost));
+	double *a2[SQT_N2D] = { out->avF_qq2, out->StdDevF_qq2, out->avF_s_qq2, out->StdDevF_s_qq2, out->avF_d_qq2, out->StdDevF_d_qq2, out->avDrTable,
+	                        out->avC2_v_rho, out->avC2_rho_v, out->avC2_v_v, out->avC2_v_mu, out->avC2_mu_v, out->avC2_mu_rho, out->avC2_rho_mu, out->avC2_mu_mu };
+	double *a1[6] = { out->rrMSDAv, out->rrMQDAv, out->rrMSDCMAv, out->rrCvvAv, out->rrCvcmvcmAv, out->rrCmmAv };
+	for (int i = 0; i < SQT_N2D; ++i) if (a2[i]) CU(cudaMemcpy(a2[i], d_blk + i * ST, sizeof(double) * ST, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 6; ++i) if (a1[i]) CU(cudaMemcpy(a1[i], d_blk + SQT_N2D * ST + i * T, sizeof(double) * T, cudaMemcpyDeviceToHost));
+	if (h->flag_s && out->rrMSR1_R_Av && out->rrMSR2_VR_Av) { // device [component][T] -> the reference's VecR3[T] / Rank2R3[T]
+		std::vector<double> tmp(12 * T);
+		CU(cudaMemcpy(tmp.data(), d_blk + SQT_N2D * ST + 6 * T, sizeof(double) * 12 * T, cudaMemcpyDeviceToHost));
+		for (size_t t = 0; t < T; ++t) {
+			for (int j = 0; j < 3; ++j) out->rrMSR1_R_Av[3 * t + j] = tmp[j * T + t];
+			for (int j = 0; j < 9; ++j) out->rrMSR2_VR_Av[9 * t + j] = tmp[(3 + j) * T + t];
+		}
+	}
 	out->countCorrAv = count;
 	out->limitCorrAv = limit;
 	out->nPtls = h->nPtls;
@@ -919,8 +1030,17 @@ extern "C" int sqt_get_kvel(sqt_handle *h, double *out)
 {
 	if (!h || !out) return SQT_ERR_ARG;
 	if (!h->flag_V) return fail(h, SQT_ERR_STATE, "sqt_get_kvel: the handle was created without flag_V");
-	return read_rho_block(h, out, h->rho_n);
+	return read_rho_block(h, out, h->blk_v * h->rho_n);
 }
+
+extern "C" int sqt_get_kmu(sqt_handle *h, double *out)
+{
+	if (!h || !out) return SQT_ERR_ARG;
+	if (!h->flag_M) return fail(h, SQT_ERR_STATE, "sqt_get_kmu: the handle was created without flag_M");
+	return read_rho_block(h, out, h->blk_m * h->rho_n);
+}
+
+extern "C" int sqt_frame_components(const sqt_handle *h) { return h ? h->ncomp : SQT_ERR_ARG; }
 
 extern "C" int sqt_profile_enable(sqt_handle *h, int enable)
 {

@@ -5,6 +5,12 @@
 #include <stdint.h>
 
 #define SQT_NVIRT 6          // virtual origin slots: (axis x,y,z) x (Re, Im) of rho(k)
+// running sums on the device (d_avblk): SQT_N2D arrays [nCS][T], then SQT_N1D arrays [T]
+//   2-D: 0 avF 1 sdF 2 avFs 3 sdFs 4 avFd 5 sdFd 6 avHist 7 C2_v_rho 8 C2_rho_v 9 C2_v_v 10 C2_v_mu 11 C2_mu_v 12 C2_mu_rho 13 C2_rho_mu 14 C2_mu_mu
+//   1-D: 0 msd 1 mqd 2 msdcm 3 cvv 4 cvcmvcm 5 cmm (never added to, like the reference) 6-8 MSR1_R x y z 9-17 MSR2_VR xx..zz
+#define SQT_N2D 15
+#define SQT_N1D 18
+#define SQT_NC2 8            // planes of bufC2, in the order of 2-D arrays 7..14
 #define SQT_MAX_WPB 4        // warps per block of the ring kernel
 
 // Everything the per-frame ring kernel needs.  Passed by value.
@@ -161,8 +167,22 @@ struct CollectiveArgs {
 	int flag_V;
 	double *kvel0;            // [B][6 nCS]
 	double *sumv0;            // [B][3]
-	double *bufC2;            // [3][B][T][nCS]: C2_v_rho, C2_rho_v, C2_v_v
+	double *bufC2;            // [SQT_NC2][B][T][nCS]: C2_v_rho, C2_rho_v, C2_v_v, C2_v_mu, C2_mu_v, C2_mu_rho, C2_rho_mu, C2_mu_mu
 	double *bufCvcm;          // [B][T]
+	// -M (flag_magnet): the dipole-weighted density kmu_q1 and its correlators, lmp2sqt.c:1556-1576
+	int flag_M;
+	double *kmu0;             // [B][6 nCS]
+	int rho_n;                // 6 nCS + 3: stride of the field blocks of rho_cur
+	int blk_v, blk_m;         // block index of kvel / kmu inside rho_cur (block 0 = rho)
+	// -s (flag_s): sumVR_ct = sum_n v (x) r of the frame (9 doubles at rho_cur + off_vr, reduced over shards),
+	// orgSumVR, rrMSR2_VR (lmp2sqt.c:1122-1142, 1273-1275, 1461-1476)
+	int flag_s;
+	int off_vr;
+	int vr_cumulative;        // no -f: the reference never zeroes sumVR_ct (ZeroOneTimeCorr runs under -f only, :1246-1249), it keeps growing
+	int vr_parity;            // sumVR_state[vr_parity] is this frame's value, [1 - vr_parity] the previous frame's
+	double *sumVR_state;      // [2][9]
+	double *orgSumVR;         // [B][9]
+	double *bufMSR2;          // [B][T][9]
 };
 int sqt_launch_collective(const CollectiveArgs &a, cudaStream_t st);
 
@@ -171,13 +191,14 @@ struct AccumArgs {
 	int nb, T, nCS;
 	const double *bufF, *bufFs, *bufMSD, *bufMQD, *bufMSDCM;
 	const int *bufHist;
-	double *cblk;             // packed block [Fs T*nCS | MSD T | MQD T | hist T*nCS | Cvv T]  (allreduced between pack and accumulate)
-	double *av[10];           // avF sdF avFs sdFs avFd sdFd avHist  avC2_v_rho avC2_rho_v avC2_v_v   [nCS][T]
-	double *av1[5];           // msd mqd msdcm  cvv cvcmvcm [T]
+	double *cblk;             // packed block [Fs T*nCS | MSD T | MQD T | hist T*nCS | Cvv T | MSR1_R 3T]  (allreduced between pack and accumulate)
+	double *av[SQT_N2D];      // [nCS][T] each, order above
+	double *av1[SQT_N1D];     // [T] each
 	// what AccumSpacetimeCorr adds depends on the getopt flags (lmp2sqt.c:381-432): F under -f, F_s / F_d under -F,
 	// DrTable under -f and -t (EvalTwoTimeEach sits inside `if (flag_t)`, :1370), MSD / MQD / MSDCM under -t
-	int flag_f, flag_F, flag_t, flag_V;
-	const double *bufC2, *bufCvv, *bufCvcm; // -V: [3][B][T][nCS], [B][T], [B][T]
+	int flag_f, flag_F, flag_t, flag_V, flag_M, flag_s;
+	const double *bufC2, *bufCvv, *bufCvcm; // -V / -M: [SQT_NC2][B][T][nCS], [B][T], [B][T]
+	const double *bufMSR1, *bufMSR2;        // -s: [B][T][3] (this shard's particles), [B][T][9]
 	int B;
 };
 int sqt_launch_pack(const AccumArgs &a, cudaStream_t st);
@@ -196,6 +217,27 @@ struct VelArgs {
 	int p, T, B;
 };
 int sqt_launch_vel(const VelArgs &a, cudaStream_t st);   // vel_ring_kernel + vel_reduce_kernel
+
+// -s: per-axis mean-square displacement over the origin ring (rrMSR1_R, lmp2sqt.c:1434-1436) and the frame's sum_n v (x) r
+struct AxisMsdArgs {
+	const double *cur;        // current positions, SoA [3][cur_pitch]
+	const double *ring;       // origin positions: element (slot, axis, particle) at slot*s_slot + axis*s_axis + particle*s_ptl
+	long long s_slot, s_axis, s_ptl;
+	double *partial;          // [B][nchunk][3]
+	double *bufMSR1;          // [B][T][3]
+	long long cur_pitch;
+	int n_local, nchunk, chunk;
+	int p, T, B;
+};
+int sqt_launch_axis_msd(const AxisMsdArgs &a, cudaStream_t st); // axis_msd_kernel + axis_msd_reduce_kernel
+struct SumVRArgs {
+	const double *cur;        // SoA: x y z at components 0..2, vx vy vz at components 3..5
+	double *partial;          // [nblocks][9]
+	double *out;              // [9]: sum_n v_a r_b, index 3 a + b (Rank2R3 order xx xy xz yx ..)
+	long long cur_pitch;
+	int n_local, nblocks;
+};
+int sqt_launch_sum_vr(const SumVRArgs &a, cudaStream_t st);     // sum_vr_kernel + sum_vr_reduce_kernel
 
 // ---- sqt_api.cu internals used by sqt_multi.cu -------------------------------------------------
 struct sqt_handle;

@@ -79,9 +79,10 @@ static int run_task(sqt_multi *m, int g, int task)
 		shard(m->n_atoms, g, m->G, &lo, &hi);
 		const size_t n = (size_t)m->n_atoms;
 		const double *s = m->soa;
-		const bool v = m->ncomp == 6;
-		int rc = sqt_push_frame_xyz(m->h[g], s + lo, s + n + lo, s + 2 * n + lo, v ? s + 3 * n + lo : nullptr, v ? s + 4 * n + lo : nullptr,
-		                            v ? s + 5 * n + lo : nullptr, hi - lo, m->n_atoms, m->xlo, m->xhi);
+		const int cv = (m->p.flag_V || m->p.flag_s) ? 3 : -1, cm = m->p.flag_M ? (cv >= 0 ? 6 : 3) : -1; // component order of the frame
+		const double *v = cv >= 0 ? s + cv * n + lo : nullptr, *u = cm >= 0 ? s + cm * n + lo : nullptr;
+		int rc = sqt_push_frame_xyz_vm(m->h[g], s + lo, s + n + lo, s + 2 * n + lo, v, v ? v + n : nullptr, v ? v + 2 * n : nullptr,
+		                               u, u ? u + n : nullptr, u ? u + 2 * n : nullptr, hi - lo, m->n_atoms, m->xlo, m->xhi);
 		if (rc >= 0 && m->stage_slot_of_push >= 0) {
 			cudaSetDevice(m->p.device + g);
 			if (cudaEventRecord(m->ev[m->stage_slot_of_push][g], sqt_internal_copy_stream(m->h[g])) != cudaSuccess) rc = SQT_ERR_CUDA;
@@ -156,7 +157,7 @@ extern "C" int sqt_multi_create(const sqt_params *p, sqt_multi **out)
 	if (p->device < 0 || p->device + G > ndev)
 		return mfail(nullptr, SQT_ERR_ARG, "sqt_multi_create: devices %d..%d requested, %d present", p->device, p->device + G - 1, ndev);
 	sqt_multi *m = new sqt_multi();
-	m->G = G; m->p = *p; m->ncomp = p->flag_V ? 6 : 3;
+	m->G = G; m->p = *p; m->ncomp = 3 + ((p->flag_V || p->flag_s) ? 3 : 0) + (p->flag_M ? 3 : 0);
 	m->h.assign(G, nullptr); m->rc.assign(G, 0);
 	m->ev[0].assign(G, nullptr); m->ev[1].assign(G, nullptr);
 	m->ev_pending[0] = m->ev_pending[1] = false;

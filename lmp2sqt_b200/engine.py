@@ -20,17 +20,39 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import SQT_FLUSH, SqtDeck, SqtParams, SqtResults
+from ._lib import SQT_FLUSH, SqtDeck, SqtFlags, SqtParams, SqtResults
 
 NAMES2D = ["avF_qq2", "StdDevF_qq2", "avF_s_qq2", "StdDevF_s_qq2", "avF_d_qq2", "StdDevF_d_qq2", "avDrTable",
-           "avC2_v_rho", "avC2_rho_v", "avC2_v_v"]          # the last three: -V only (zero otherwise)
-NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv", "rrCvvAv", "rrCvcmvcmAv"]
+           "avC2_v_rho", "avC2_rho_v", "avC2_v_v",           # -V only (zero otherwise)
+           "avC2_v_mu", "avC2_mu_v", "avC2_mu_rho", "avC2_rho_mu", "avC2_mu_mu"]   # -M (the first two: -V -M) only
+NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv", "rrCvvAv", "rrCvcmvcmAv", "rrCmmAv"]
+NAMES_TENSOR = {"rrMSR1_R_Av": 3, "rrMSR2_VR_Av": 9}         # -s only: the reference's VecR3[T] / Rank2R3[T]
 
 
 def _flag_ints(flags: str):
-    """getopt flags of the reference (lmp2sqt.c:152-191): -F implies -f."""
+    """getopt flags of the reference (lmp2sqt.c:152-191) as (f, F, t, V, M, s): -F implies -f, -s implies -t."""
     f_F = "F" in flags
-    return int(f_F or "f" in flags), int(f_F), int("t" in flags), int("V" in flags)
+    return (int(f_F or "f" in flags), int(f_F), int("t" in flags or "s" in flags), int("V" in flags), int("M" in flags),
+            int("s" in flags))
+
+
+def _ncomp(flags: str) -> int:
+    """arrays per SoA frame: x y z, then vx vy vz (-V or -s), then mux muy muz (-M)"""
+    return 3 + (3 if ("V" in flags or "s" in flags) else 0) + (3 if "M" in flags else 0)
+
+
+def _fill_stage(st: np.ndarray, flags: str, xyz, vel, mu) -> None:
+    st[:3] = np.asarray(xyz, dtype=np.float64).T
+    c = 3
+    if "V" in flags or "s" in flags:
+        if vel is None:
+            raise SqtError("-V / -s need velocities")
+        st[c:c + 3] = np.asarray(vel, dtype=np.float64).T
+        c += 3
+    if "M" in flags:
+        if mu is None:
+            raise SqtError("-M needs dipoles")
+        st[c:c + 3] = np.asarray(mu, dtype=np.float64).T
 
 
 class SqtError(RuntimeError):
@@ -84,11 +106,11 @@ class Results:
 
     def array(self, name: str) -> np.ndarray:
         p = getattr(self.c, name)
-        shape = (self.S, self.T) if name in NAMES2D else (self.T,)
+        shape = (self.S, self.T) if name in NAMES2D else ((self.T, NAMES_TENSOR[name]) if name in NAMES_TENSOR else (self.T,))
         return np.ctypeslib.as_array(p, shape=shape)
 
     def to_dict(self) -> dict:
-        d = {n: self.array(n).copy() for n in NAMES2D + NAMES1D}
+        d = {n: self.array(n).copy() for n in NAMES2D + NAMES1D + list(NAMES_TENSOR)}
         for k in ("countCorrAv", "limitCorrAv", "nPtls", "g_Vol", "kVal", "first_Vol", "first_limitCorrAv", "number_call_print"):
             d[k] = getattr(self.c, k)
         return d
@@ -96,12 +118,14 @@ class Results:
     def normalise(self, deck: Deck, flags: str = "Ft") -> None:
         """prePrintProcess (lmp2sqt.c:576-675), in place."""
         dk = deck.to_c()
-        _lib.host_lib().sqt_host_normalise_v(C.byref(self.c), C.byref(dk), *_flag_ints(flags))
+        fl = SqtFlags(*_flag_ints(flags))
+        _lib.host_lib().sqt_host_normalise_x(C.byref(self.c), C.byref(dk), C.byref(fl))
 
     def print_process(self, outdir: str, deck: Deck, flags: str = "Ft", date: str | None = None) -> None:
         """PrintProcess (lmp2sqt.c:338-367): normalise in place and write the reference's files into ``outdir``."""
         dk = deck.to_c()
-        rc = _lib.host_lib().sqt_host_print_process_v(os.fsencode(outdir), C.byref(self.c), C.byref(dk), *_flag_ints(flags),
+        fl = SqtFlags(*_flag_ints(flags))
+        rc = _lib.host_lib().sqt_host_print_process_x(os.fsencode(outdir), C.byref(self.c), C.byref(dk), C.byref(fl),
                                                       date.encode() if date else None)
         if rc:
             raise OSError("sqt_host_print_process failed in %s" % outdir)
@@ -114,10 +138,10 @@ class SpacetimeCorr:
         self.lib = _lib.engine_lib()
         self.deck = deck
         self.flags = flags
-        ff, fF, ft, fV = _flag_ints(flags)
+        ff, fF, ft, fV, fM, fs = _flag_ints(flags)
         p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
-                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, 0, fV)
-        self.ncomp = 6 if fV else 3
+                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, 0, fV, fM, fs)
+        self.ncomp = _ncomp(flags)
         h = C.c_void_p()
         rc = self.lib.sqt_create(C.byref(p), C.byref(h))
         if rc:
@@ -160,16 +184,13 @@ class SpacetimeCorr:
             raise SqtError("sqt_stage_acquire: " + self.lib.sqt_last_error(self.h).decode())
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.ncomp, n_local))
 
-    def EvalSpacetimeCorr(self, xyz: np.ndarray, xlo: float, xhi: float, n_total: int | None = None, vel: np.ndarray | None = None) -> int:
-        """One frame.  ``xyz`` is (n, 3) atoms in dump order (this rank's shard); ``vel`` likewise with -V.  Returns
-        SQT_FLUSH (1) when the reference would have called PrintProcess inside AccumSpacetimeCorr."""
+    def EvalSpacetimeCorr(self, xyz: np.ndarray, xlo: float, xhi: float, n_total: int | None = None, vel: np.ndarray | None = None,
+                          mu: np.ndarray | None = None) -> int:
+        """One frame.  ``xyz`` is (n, 3) atoms in dump order (this rank's shard); ``vel`` likewise with -V / -s, ``mu`` with
+        -M.  Returns SQT_FLUSH (1) when the reference would have called PrintProcess inside AccumSpacetimeCorr."""
         n = xyz.shape[0]
         st = self.stage(n)
-        st[:3] = np.asarray(xyz, dtype=np.float64).T
-        if self.ncomp == 6:
-            if vel is None:
-                raise SqtError("-V needs velocities")
-            st[3:] = np.asarray(vel, dtype=np.float64).T
+        _fill_stage(st, self.flags, xyz, vel, mu)
         return self.push_staged(st, n, n_total if n_total is not None else n, xlo, xhi)
 
     push_frame = EvalSpacetimeCorr
@@ -223,6 +244,11 @@ class SpacetimeCorr:
         self._check(self.lib.sqt_get_kvel(self.h, out.ctypes.data), "sqt_get_kvel")
         return out
 
+    def kmu(self) -> np.ndarray:
+        out = np.zeros((3, self.S, 2))
+        self._check(self.lib.sqt_get_kmu(self.h, out.ctypes.data), "sqt_get_kmu")
+        return out
+
     @property
     def kernel_launches(self) -> int:
         return self.lib.sqt_kernel_launches(self.h)
@@ -259,10 +285,10 @@ class MultiSpacetimeCorr:
     def __init__(self, deck: Deck, flags: str = "Ft", n_gpus: int = 2, device: int = 0):
         self.lib = _lib.engine_lib()
         self.deck, self.flags = deck, flags
-        ff, fF, ft, fV = _flag_ints(flags)
+        ff, fF, ft, fV, fM, fs = _flag_ints(flags)
         p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
-                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, n_gpus, fV)
-        self.ncomp = 6 if fV else 3
+                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, n_gpus, fV, fM, fs)
+        self.ncomp = _ncomp(flags)
         h = C.c_void_p()
         rc = self.lib.sqt_multi_create(C.byref(p), C.byref(h))
         if rc:
@@ -292,15 +318,13 @@ class MultiSpacetimeCorr:
     def InitSpacetimeCorr(self):
         self._check(self.lib.sqt_multi_begin_file(self.h), "sqt_multi_begin_file")
 
-    def EvalSpacetimeCorr(self, xyz, xlo, xhi, n_total=None, vel=None) -> int:
+    def EvalSpacetimeCorr(self, xyz, xlo, xhi, n_total=None, vel=None, mu=None) -> int:
         n = xyz.shape[0]
         p = self.lib.sqt_multi_stage_acquire(self.h, n)
         if not p:
             raise SqtError("sqt_multi_stage_acquire: " + self.lib.sqt_multi_last_error(self.h).decode())
         st = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.ncomp, n))
-        st[:3] = np.asarray(xyz, dtype=np.float64).T
-        if self.ncomp == 6:
-            st[3:] = np.asarray(vel, dtype=np.float64).T
+        _fill_stage(st, self.flags, xyz, vel, mu)
         return self._check(self.lib.sqt_multi_push_frame(self.h, st.ctypes.data, n, float(xlo), float(xhi)), "sqt_multi_push_frame")
 
     def fetch(self) -> Results:
@@ -424,7 +448,7 @@ def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank
             eng.comm_init(unique_id, rank, nranks)
     eng.set_limit(limit)
     printed = None
-    with_v = "V" in flags
+    with_v, with_m = ("V" in flags or "s" in flags), "M" in flags
     for t, u in zip(trajs, use):
         if not u:
             continue
@@ -432,7 +456,7 @@ def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank
         lo, hi = shard_bounds(t.n_atoms, rank, nranks)
         for f in range(t.n_frames):
             rc = eng.EvalSpacetimeCorr(t.positions[f, lo:hi], t.box[f, 0, 0], t.box[f, 0, 1], n_total=t.n_atoms,
-                                       vel=t.velocities[f, lo:hi] if with_v else None)
+                                       vel=t.velocities[f, lo:hi] if with_v else None, mu=t.dipoles[f, lo:hi] if with_m else None)
             if rc == SQT_FLUSH:
                 printed = eng.fetch()
                 if on_flush:

@@ -43,6 +43,32 @@ class Trajectory:
     timesteps: np.ndarray
     types: np.ndarray
     velocities: np.ndarray | None = None   # [f, n, 3]; only dumps written with ``velocities=True`` carry them
+    _dipoles_raw: np.ndarray | None = None
+
+    @property
+    def dipoles_raw(self) -> np.ndarray:
+        """[f, n, 3] dipole vectors as a dump carries them (``mux muy muz`` at ``%.6f``, length about 1.3): a slow rotational
+        random walk per particle; made on first use from a generator of their own, so the positions and velocities of a
+        seed never depend on whether the dipoles were asked for."""
+        if self._dipoles_raw is None:
+            rng = np.random.Generator(np.random.PCG64(977 + 31 * self.n_atoms + self.n_frames))
+            f, n = self.n_frames, self.n_atoms
+            mu = np.empty((f, n, 3))
+            m = rng.normal(0.0, 1.0, size=(n, 3))
+            for i in range(f):
+                m = m / np.linalg.norm(m, axis=1, keepdims=True)
+                mu[i] = 1.3 * m
+                m = m + 0.25 * rng.normal(0.0, 1.0, size=(n, 3))
+            self._dipoles_raw = np.round(mu, 6)
+        return self._dipoles_raw
+
+    @property
+    def dipoles(self) -> np.ndarray:
+        """[f, n, 3] what the reference's reader keeps of them: unit vectors, normalised with its own operation order
+        (make_atom_dipole, snapshot.c:440-459)."""
+        r = self.dipoles_raw
+        mu1 = np.sqrt(r[..., 0] * r[..., 0] + r[..., 1] * r[..., 1] + r[..., 2] * r[..., 2])
+        return r / mu1[..., None]
 
     @property
     def n_frames(self) -> int:
@@ -148,9 +174,10 @@ def cubic_lattice_trajectory(n_side: int, n_frames: int, a: float = 1.0) -> Traj
     return Trajectory(pos, box, np.arange(n_frames, dtype=np.int64), np.ones(len(p0), dtype=np.int32))
 
 
-def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None, velocities: bool = False) -> None:
+def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None, velocities: bool = False, dipoles: bool = False) -> None:
     """Write ``traj`` as a LAMMPS text dump (``%.6f`` coordinates, ids 1..N in fixed order); ``velocities`` adds the
-    ``vx vy vz`` columns (the reference's second accepted header, snapshot.c:296-331)."""
+    ``vx vy vz`` columns, ``dipoles`` the ``mux muy muz`` columns (before the velocities): the reference's other accepted
+    headers (snapshot.c:263-331)."""
     own = isinstance(path_or_file, (str, os.PathLike))
     f = open(path_or_file, "w") if own else path_or_file
     try:
@@ -162,13 +189,14 @@ def write_text_dump(traj: Trajectory, path_or_file, frames: slice | None = None,
             f.write("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % (traj.timesteps[fi], n))
             for a in range(3):
                 f.write("%.6f %.6f\n" % (b[a, 0], b[a, 1]))
-            f.write("ITEM: ATOMS id type xu yu zu vx vy vz\n" if velocities else "ITEM: ATOMS id type xu yu zu\n")
+            f.write("ITEM: ATOMS id type xu yu zu" + (" mux muy muz" if dipoles else "") + (" vx vy vz" if velocities else "") + "\n")
             buf = io.StringIO()
-            p = traj.positions[fi]
+            cols = [ids, traj.types, traj.positions[fi]]
+            if dipoles:
+                cols.append(traj.dipoles_raw[fi])
             if velocities:
-                np.savetxt(buf, np.column_stack([ids, traj.types, p, traj.velocities[fi]]), fmt="%d %d %.6f %.6f %.6f %.6f %.6f %.6f")
-            else:
-                np.savetxt(buf, np.column_stack([ids, traj.types, p]), fmt="%d %d %.6f %.6f %.6f")
+                cols.append(traj.velocities[fi])
+            np.savetxt(buf, np.column_stack(cols), fmt="%d %d" + " %.6f" * (3 * (len(cols) - 2)))
             f.write(buf.getvalue())
     finally:
         if own:

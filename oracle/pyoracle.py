@@ -36,6 +36,28 @@ NAMES1D = ["rrMSDAv", "rrMQDAv", "rrMSDCMAv"]
 # -V (flag_velocity) adds these (oracle array indices 7..9 and 3..4)
 NAMES2D_V = ["avC2_v_rho", "avC2_rho_v", "avC2_v_v"]
 NAMES1D_V = ["rrCvvAv", "rrCvcmvcmAv"]
+# -M (flag_magnet): oracle 2-D indices 10..14 (10, 11 only with -V as well) and 1-D index 5 (rrCmmAv: allocated, zeroed, printed,
+# never added to -- lmp2sqt.c:420-432 has no line for it)
+NAMES2D_VM = ["avC2_v_mu", "avC2_mu_v"]
+NAMES2D_M = ["avC2_mu_rho", "avC2_rho_mu", "avC2_mu_mu"]
+NAMES1D_M = ["rrCmmAv"]
+# -s (flag_s): oracle 1-D indices 6..17 raw (+ 18, 19 in the printed set): rrMSR1_R_Av [T][3], rrMSR2_VR_Av [T][9]
+NAMES1D_S = ["rrMSR1_R_Av", "rrMSR2_VR_Av"]
+
+
+def names_for(flags):
+    """(2-D names with their oracle index, 1-D names with index) of a flag set."""
+    n2 = list(enumerate(NAMES2D))
+    n1 = list(enumerate(NAMES1D))
+    if "V" in flags:
+        n2 += [(7 + i, n) for i, n in enumerate(NAMES2D_V)]
+        n1 += [(3 + i, n) for i, n in enumerate(NAMES1D_V)]
+    if "V" in flags and "M" in flags:
+        n2 += [(10 + i, n) for i, n in enumerate(NAMES2D_VM)]
+    if "M" in flags:
+        n2 += [(12 + i, n) for i, n in enumerate(NAMES2D_M)]
+        n1 += [(5, "rrCmmAv")]
+    return n2, n1
 
 
 def build(force: bool = False) -> None:
@@ -53,14 +75,15 @@ def have_reference() -> bool:
 class _Params(C.Structure):
     _fields_ = [("kVal", C.c_double), ("deltaT", C.c_double), ("mass", C.c_double), ("rVal", C.c_double),
                 ("limitCorrAv", C.c_int), ("nCBuffer", C.c_int), ("nCSpatial", C.c_int), ("nCTime", C.c_int),
-                ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int), ("flag_V", C.c_int)]
+                ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int), ("flag_V", C.c_int),
+                ("flag_M", C.c_int), ("flag_s", C.c_int)]
 
 
 class OraclePort:
     """The plain-C restatement.  Method names follow the reference's call seam."""
 
     def __init__(self, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=0, deltaT=0.06,
-                 kVal=0.0981748, mass=1.0, flag_f=True, flag_F=True, flag_t=True, flag_V=False):
+                 kVal=0.0981748, mass=1.0, flag_f=True, flag_F=True, flag_t=True, flag_V=False, flag_M=False, flag_s=False):
         build()
         L = C.CDLL(PORT_SO)
         L.sqt_oracle_create.restype = C.c_void_p
@@ -70,6 +93,7 @@ class OraclePort:
             getattr(L, fn).restype = None
         L.sqt_oracle_push_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.sqt_oracle_push_frame_v.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.sqt_oracle_push_frame_vm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.sqt_oracle_finish.argtypes = [C.c_void_p]
         L.sqt_oracle_set_limit.argtypes = [C.c_void_p, C.c_int]
         L.sqt_oracle_set_limit.restype = None
@@ -97,11 +121,10 @@ class OraclePort:
         self.S, self.T = nCSpatial, nCTime
         self.B = max(1, min(nCBuffer, nCTime))
         p = _Params(kVal, deltaT, mass, rVal, limitCorrAv, nCBuffer, nCSpatial, nCTime, nCSkip,
-                    int(flag_f), int(flag_F), int(flag_t), int(flag_V))
+                    int(flag_f), int(flag_F), int(flag_t), int(flag_V), int(flag_M), int(flag_s))
         self.h = L.sqt_oracle_create(C.byref(p))
-        self.flag_V = bool(flag_V)
-        self.names2d = NAMES2D + (NAMES2D_V if flag_V else [])
-        self.names1d = NAMES1D + (NAMES1D_V if flag_V else [])
+        self.flag_V, self.flag_M, self.flag_s = bool(flag_V), bool(flag_M), bool(flag_s)
+        self.names2d, self.names1d = names_for(("V" if flag_V else "") + ("M" if flag_M else ""))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -111,9 +134,14 @@ class OraclePort:
     def begin_file(self):
         self.L.sqt_oracle_begin_file(self.h)
 
-    def push_frame(self, xyz: np.ndarray, xlo: float, xhi: float, vel: np.ndarray | None = None) -> int:
+    def push_frame(self, xyz: np.ndarray, xlo: float, xhi: float, vel: np.ndarray | None = None, mu: np.ndarray | None = None) -> int:
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
-        if vel is not None:
+        if mu is not None:
+            mu = np.ascontiguousarray(mu, dtype=np.float64)
+            vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
+            rc = self.L.sqt_oracle_push_frame_vm(self.h, xyz.ctypes.data, None if vel is None else vel.ctypes.data, mu.ctypes.data,
+                                                 xyz.shape[0], float(xlo), float(xhi))
+        elif vel is not None:
             vel = np.ascontiguousarray(vel, dtype=np.float64)
             rc = self.L.sqt_oracle_push_frame_v(self.h, xyz.ctypes.data, vel.ctypes.data, xyz.shape[0], float(xlo), float(xhi))
         else:
@@ -147,23 +175,31 @@ class OraclePort:
         p = getattr(self.L, "sqt_oracle_" + fn)(self.h, which)
         return np.ctypeslib.as_array(p, shape=shape).copy()
 
+    def _set(self, kind) -> dict:
+        d = {n: self._arr(kind + "2d", i, (self.S, self.T)) for i, n in self.names2d}
+        d.update({n: self._arr(kind + "1d", i, (self.T,)) for i, n in self.names1d})
+        if self.flag_s:   # the reference's VecR3 / Rank2R3 arrays: [T][3] and [T][9] (xx xy xz yx yy yz zx zy zz)
+            d["rrMSR1_R_Av"] = np.stack([self._arr(kind + "1d", 6 + j, (self.T,)) for j in range(3)], axis=1)
+            d["rrMSR2_VR_Av"] = np.stack([self._arr(kind + "1d", 9 + j, (self.T,)) for j in range(9)], axis=1)
+            if kind == "printed":
+                d["rrMSR2_VR_Av_dig"] = self._arr("printed1d", 18, (self.T,))
+                d["rrMSR2_VR_Av_offdig"] = self._arr("printed1d", 19, (self.T,))
+        return d
+
     def raw(self) -> dict:
-        d = {n: self._arr("raw2d", i, (self.S, self.T)) for i, n in enumerate(self.names2d)}
-        d.update({n: self._arr("raw1d", i, (self.T,)) for i, n in enumerate(self.names1d)})
+        d = self._set("raw")
         d["countCorrAv"] = self.countCorrAv
         return d
 
     def printed(self) -> dict:
-        d = {n: self._arr("printed2d", i, (self.S, self.T)) for i, n in enumerate(self.names2d)}
-        d.update({n: self._arr("printed1d", i, (self.T,)) for i, n in enumerate(self.names1d)})
+        d = self._set("printed")
         d["countCorrAv"] = self.printed_count
         d["kVal"] = self.kVal
         return d
 
     def printed_raw(self) -> dict:
         """Raw sums at the moment of the last print + the scalars the host normalisation needs."""
-        d = {n: self._arr("printed_raw2d", i, (self.S, self.T)) for i, n in enumerate(self.names2d)}
-        d.update({n: self._arr("printed_raw1d", i, (self.T,)) for i, n in enumerate(self.names1d)})
+        d = self._set("printed_raw")
         d.update(countCorrAv=self.printed_count, kVal=self.kVal, nPtls=self.L.sqt_oracle_nPtls(self.h),
                  first_Vol=self.L.sqt_oracle_first_vol(self.h), first_limitCorrAv=self.L.sqt_oracle_first_limit(self.h),
                  g_Vol=self.L.sqt_oracle_vol(self.h), limitCorrAv=self.L.sqt_oracle_limitCorrAv(self.h))
@@ -186,7 +222,11 @@ def run_port(traj, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=
     flag_f = flag_F or "f" in flags
     flag_t = "t" in flags
     flag_V = "V" in flags
-    o = OraclePort(nCSpatial, nCTime, nCBuffer, nCSkip, rVal, 0, flag_f=flag_f, flag_F=flag_F, flag_t=flag_t, flag_V=flag_V)
+    flag_M = "M" in flags
+    flag_s = "s" in flags
+    flag_t = flag_t or flag_s   # getopt: -s switches -t on as well (lmp2sqt.c:156-160)
+    o = OraclePort(nCSpatial, nCTime, nCBuffer, nCSkip, rVal, 0, flag_f=flag_f, flag_F=flag_F, flag_t=flag_t, flag_V=flag_V,
+                   flag_M=flag_M, flag_s=flag_s)
     limit = limitCorrAv
     B = min(nCBuffer, nCTime)
     use = []
@@ -205,7 +245,8 @@ def run_port(traj, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, limitCorrAv=
             continue
         o.begin_file()
         for f in range(t.n_frames):
-            rc = o.push_frame(t.positions[f], t.box[f, 0, 0], t.box[f, 0, 1], vel=t.velocities[f] if flag_V else None)
+            rc = o.push_frame(t.positions[f], t.box[f, 0, 0], t.box[f, 0, 1], vel=t.velocities[f] if (flag_V or flag_s) else None,
+                              mu=t.dipoles[f] if flag_M else None)
             log.append((o.countCorrAv, tuple(o.buffer_counts())))
             if rc == 1:
                 printed = o.printed()
@@ -263,9 +304,12 @@ class ReferenceLib:
         flag_F = "F" in flags
         g("flag_F", C.c_bool).value = flag_F
         g("flag_f", C.c_bool).value = flag_F or ("f" in flags)
-        g("flag_t", C.c_bool).value = "t" in flags
-        self.flag_V = "V" in flags
+        self.flag_V, self.flag_M, self.flag_s = "V" in flags, "M" in flags, "s" in flags
+        g("flag_t", C.c_bool).value = ("t" in flags) or self.flag_s   # getopt, lmp2sqt.c:156-160
         g("flag_velocity", C.c_bool).value = self.flag_V
+        g("flag_magnet", C.c_bool).value = self.flag_M
+        g("flag_s", C.c_bool).value = self.flag_s
+        self.flags = flags
         self.S, self.T, self.B = nCSpatial, nCTime, max(1, min(nCBuffer, nCTime))
         self.cl = _MakeSqtClass()
         C.c_void_p.in_dll(L, "classSqt").value = C.addressof(self.cl)
@@ -281,7 +325,7 @@ class ReferenceLib:
     def begin_file(self):
         self.L.InitSpacetimeCorr(C.byref(self.cl))
 
-    def push_frame(self, xyz: np.ndarray, xlo, xhi, box_yz=None, vel=None) -> float:
+    def push_frame(self, xyz: np.ndarray, xlo, xhi, box_yz=None, vel=None, mu=None) -> float:
         """EvalSpacetimeCorr on a Snapshot built from ``xyz`` (and ``vel``); returns the call's wall seconds."""
         n = xyz.shape[0]
         atoms = np.zeros(n, dtype=ATOM_DTYPE)
@@ -290,6 +334,8 @@ class ReferenceLib:
         atoms["x"], atoms["y"], atoms["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
         if vel is not None:
             atoms["vx"], atoms["vy"], atoms["vz"] = vel[:, 0], vel[:, 1], vel[:, 2]
+        if mu is not None:
+            atoms["mux"], atoms["muy"], atoms["muz"] = mu[:, 0], mu[:, 1], mu[:, 2]
         snap = _Snapshot()
         snap.timestep = 0
         snap.NumAtoms = n
@@ -325,11 +371,15 @@ class ReferenceLib:
     def arrays(self) -> dict:
         m = {"avF": "avF_qq2", "StdDevF": "StdDevF_qq2", "avF_s": "avF_s_qq2", "StdDevF_s": "StdDevF_s_qq2",
              "avF_d": "avF_d_qq2", "StdDevF_d": "StdDevF_d_qq2", "avDrTable": "avDrTable"}
-        if self.flag_V:
-            m.update({k: k for k in NAMES2D_V})
+        n2, n1 = names_for(self.flags)
+        m.update({k: k for _, k in n2 if k not in NAMES2D})
         d = {k: self._a2(v) for k, v in m.items()}
-        for n in NAMES1D + (NAMES1D_V if self.flag_V else []):
+        for _, n in n1:
             d[n] = self._a1(n)
+        if self.flag_s:   # VecR3[T], Rank2R3[T]
+            for name, w in (("rrMSR1_R_Av", 3), ("rrMSR2_VR_Av", 9), ("rrMSR2_VR_Av_dig", 1), ("rrMSR2_VR_Av_offdig", 1)):
+                p = C.POINTER(C.c_double).in_dll(self.L, name)
+                d[name] = np.ctypeslib.as_array(p, shape=(self.T, w) if w > 1 else (self.T,)).copy()
         d["countCorrAv"] = self.countCorrAv
         d["kVal"] = self._g("kVal", C.c_double).value
         return d
@@ -346,10 +396,10 @@ def _ref_worker(job_path: str) -> None:
     ref = ReferenceLib(**job["params"])
     ref.set_limit(job["limit"])
     times, log = [], []
-    for pos, box, vel in job["files"]:
+    for pos, box, vel, mu in job["files"]:
         ref.begin_file()
         for fi in range(pos.shape[0]):
-            dt = ref.push_frame(pos[fi], box[fi, 0, 0], box[fi, 0, 1], vel=None if vel is None else vel[fi])
+            dt = ref.push_frame(pos[fi], box[fi, 0, 0], box[fi, 0, 1], vel=None if vel is None else vel[fi], mu=None if mu is None else mu[fi])
             times.append(dt)
             log.append(ref.countCorrAv)
     raw = ref.arrays()
@@ -373,7 +423,8 @@ def run_reference(trajs, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, flags=
     with tempfile.TemporaryDirectory() as td:
         job = {"cwd": td, "out": os.path.join(td, "out.pkl"), "limit": int(limit), "normalise": normalise,
                "params": dict(nCSpatial=nCSpatial, nCTime=nCTime, nCBuffer=nCBuffer, nCSkip=nCSkip, rVal=rVal, flags=flags),
-               "files": [(t.positions, t.box, t.velocities if "V" in flags else None) for t in trajs]}
+               "files": [(t.positions, t.box, t.velocities if ("V" in flags or "s" in flags) else None,
+                          t.dipoles if "M" in flags else None) for t in trajs]}
         jp = os.path.join(td, "job.pkl")
         with open(jp, "wb") as f:
             pickle.dump(job, f)
@@ -389,9 +440,13 @@ def run_reference(trajs, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, flags=
             return pickle.load(f)
 
 
-def run_reference_cli(workdir, deck_name, dump_names, flags=("-F", "-t"), threads=1) -> subprocess.CompletedProcess:
-    """Run the unmodified reference *binary* in ``workdir`` (it writes its outputs and rewrites the deck there)."""
+def run_reference_cli(workdir, deck_name, dump_names, flags=("-F", "-t"), threads=1, zero_heap=False) -> subprocess.CompletedProcess:
+    """Run the unmodified reference *binary* in ``workdir`` (it writes its outputs and rewrites the deck there).
+    ``zero_heap``: glibc hands out zero-filled blocks (see run_reference) -- the reference never initialises TBuf.rrMSDCM, and
+    on some runs the MSDCM column of its Dt file is whatever the heap held."""
     env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    if zero_heap:
+        env.update(MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0")
     return subprocess.run([REF_BIN, *flags, "-i", deck_name, *dump_names], cwd=workdir, env=env,
                           capture_output=True, text=True)
 

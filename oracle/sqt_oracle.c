@@ -24,8 +24,8 @@
 #endif
 
 #define NAX 3 /* N_AXIS, lmp2sqt.h:103 */
-#define N2D 10
-#define N1D 5
+#define N2D 15
+#define N1D 20
 
 typedef struct {
 	/* per-origin copies, SetWaitedTimeCorr lmp2sqt.c:1260-1314 */
@@ -42,6 +42,15 @@ typedef struct {
 	double *org_kvel;  /* [6 nCS]     org_kvel_q1   */
 	double *Cvrho, *Crhov, *Cvv2; /* [nCS][T]  C2_v_rho, C2_rho_v, C2_v_v */
 	double *cvv, *cvcm;           /* [T]       rrCvv, rrCvcmvcm */
+	/* -M (flag_magnet): dipole-weighted density and its correlators */
+	double *org_kmu;   /* [6 nCS]     org_kmu_q1    */
+	double *Cvmu, *Cmuv, *Cmurho, *Crhomu, *Cmumu; /* [nCS][T]  C2_v_mu, C2_mu_v, C2_mu_rho, C2_rho_mu, C2_mu_mu */
+	double *cmm;       /* [T] rrCmm (computed per buffer, never accumulated by AccumSpacetimeCorr: lmp2sqt.c:420-432) */
+	double *org_mu;    /* [N][3]      orgMu         */
+	/* -s (flag_s): per-axis MSD and the squared change of sum_n v (x) r */
+	double *msr1;      /* [T][3]  rrMSR1_R  */
+	double *msr2;      /* [T][9]  rrMSR2_VR */
+	double org_sumVR[9];
 	int count;
 } ring_buf;
 
@@ -56,10 +65,13 @@ struct sqt_oracle {
 	/* current frame (tBuf[0] scratch in the reference, lmp2sqt.c:1098-1102) */
 	double *rho, *tmp_row, *self, *dist;
 	double *kvel;      /* [6 nCS] kvel_q1: sum_n (q v_a) (-sin, cos)(q r_a), lmp2sqt.c:1203-1208 */
-	const double *cur_xyz, *cur_vel;
-	/* running sums: 0 avF 1 StdDevF 2 avF_s 3 StdDevF_s 4 avF_d 5 StdDevF_d 6 avDrTable 7 avC2_v_rho 8 avC2_rho_v 9 avC2_v_v */
+	double *kmu;       /* [6 nCS] kmu_q1, the same with the dipole components, :1209-1214 */
+	double sumVR[9];   /* sumVR_ct: sum_n v (x) r, EvalOneTimeSumVR :1122-1142; zeroed only by ZeroOneTimeCorr, i.e. under -f (:1120) */
+	const double *cur_xyz, *cur_vel, *cur_mu;
+	/* running sums: 0 avF 1 StdDevF 2 avF_s 3 StdDevF_s 4 avF_d 5 StdDevF_d 6 avDrTable 7 avC2_v_rho 8 avC2_rho_v 9 avC2_v_v
+	 * 10 avC2_v_mu 11 avC2_mu_v 12 avC2_mu_rho 13 avC2_rho_mu 14 avC2_mu_mu */
 	double *sum2d[N2D], *out2d[N2D], *rawp2d[N2D]; /* running sums, normalised at last print, raw at last print */
-	double *sum1d[N1D], *out1d[N1D], *rawp1d[N1D]; /* 0 MSD 1 MQD 2 MSDCM 3 Cvv 4 Cvcmvcm */
+	double *sum1d[N1D], *out1d[N1D], *rawp1d[N1D]; /* 0 MSD 1 MQD 2 MSDCM 3 Cvv 4 Cvcmvcm 5 Cmm 6-8 MSR1_R x y z 9-17 MSR2_VR xx..zz 18 dig 19 offdig */
 	double first_vol; int first_limit;
 	double *factorDr;
 };
@@ -86,11 +98,16 @@ sqt_oracle *sqt_oracle_create(const sqt_oracle_params *p)
 		b->org_kvel = zalloc(2 * NAX * S);
 		b->Cvrho = zalloc((size_t)S * T); b->Crhov = zalloc((size_t)S * T); b->Cvv2 = zalloc((size_t)S * T);
 		b->cvv = zalloc(T); b->cvcm = zalloc(T);
+		b->org_kmu = zalloc(2 * NAX * S);
+		b->Cvmu = zalloc((size_t)S * T); b->Cmuv = zalloc((size_t)S * T); b->Cmurho = zalloc((size_t)S * T);
+		b->Crhomu = zalloc((size_t)S * T); b->Cmumu = zalloc((size_t)S * T);
+		b->cmm = zalloc(T); b->msr1 = zalloc((size_t)T * 3); b->msr2 = zalloc((size_t)T * 9);
 	}
 	for (int i = 0; i < N2D; i++) { o->sum2d[i] = zalloc((size_t)S * T); o->out2d[i] = zalloc((size_t)S * T); o->rawp2d[i] = zalloc((size_t)S * T); }
 	for (int i = 0; i < N1D; i++) { o->sum1d[i] = zalloc(T); o->out1d[i] = zalloc(T); o->rawp1d[i] = zalloc(T); }
 	o->rho = zalloc(2 * NAX * S);
 	o->kvel = zalloc(2 * NAX * S);
+	o->kmu = zalloc(2 * NAX * S);
 	o->tmp_row = zalloc(2 * NAX * S);
 	o->factorDr = zalloc(S);
 	return o;
@@ -104,11 +121,13 @@ void sqt_oracle_destroy(sqt_oracle *o)
 		free(b->F); free(b->Fs); free(b->Fd); free(b->hist); free(b->msd); free(b->mqd);
 		free(b->msdcm); free(b->org_rho); free(b->org_pos); free(b->org_self); free(b->org_dist);
 		free(b->org_vel); free(b->org_kvel); free(b->Cvrho); free(b->Crhov); free(b->Cvv2); free(b->cvv); free(b->cvcm);
+		free(b->org_kmu); free(b->Cvmu); free(b->Cmuv); free(b->Cmurho); free(b->Crhomu); free(b->Cmumu); free(b->cmm); free(b->org_mu);
+		free(b->msr1); free(b->msr2);
 	}
 	free(o->buf);
 	for (int i = 0; i < N2D; i++) { free(o->sum2d[i]); free(o->out2d[i]); free(o->rawp2d[i]); }
 	for (int i = 0; i < N1D; i++) { free(o->sum1d[i]); free(o->out1d[i]); free(o->rawp1d[i]); }
-	free(o->rho); free(o->kvel); free(o->tmp_row); free(o->self); free(o->dist); free(o->factorDr);
+	free(o->rho); free(o->kvel); free(o->kmu); free(o->tmp_row); free(o->self); free(o->dist); free(o->factorDr);
 	free(o);
 }
 
@@ -134,6 +153,7 @@ static void alloc_more(sqt_oracle *o)
 	for (int nb = 0; nb < B; nb++) {
 		o->buf[nb].org_pos = zalloc((size_t)N * 3);
 		o->buf[nb].org_vel = zalloc((size_t)N * 3);
+		o->buf[nb].org_mu = zalloc((size_t)N * 3);
 		o->buf[nb].org_self = zalloc(N * row);
 		o->buf[nb].org_dist = zalloc(N * row);
 	}
@@ -152,7 +172,8 @@ static void one_time_kspace(sqt_oracle *o)
 	const int S = o->p.nCSpatial, N = o->N;
 	const int row = 2 * NAX * S;
 	const double kVal = o->kVal;
-	for (int j = 0; j < row; j++) { o->rho[j] = 0.; if (o->p.flag_V) o->kvel[j] = 0.; }
+	for (int j = 0; j < row; j++) { o->rho[j] = 0.; if (o->p.flag_V) o->kvel[j] = 0.; if (o->p.flag_M) o->kmu[j] = 0.; }
+	for (int j = 0; j < 9; j++) o->sumVR[j] = 0.; /* :1120 */
 	if (o->p.flag_F) {
 		memset(o->self, 0, sizeof(double) * (size_t)N * row);
 		memset(o->dist, 0, sizeof(double) * (size_t)N * row);
@@ -184,6 +205,12 @@ static void one_time_kspace(sqt_oracle *o)
 					o->kvel[mR] += -kv * s;
 					o->kvel[mI] += +kv * c;
 				}
+				if (o->p.flag_M) { /* :1209-1214 */
+					const int qn = m + 1;
+					const double km = qn * kVal * o->cur_mu[3 * (size_t)n + k];
+					o->kmu[mR] += -km * s;
+					o->kmu[mI] += +km * c;
+				}
 				o->tmp_row[mR] = c;
 				o->tmp_row[mI] = s;
 			}
@@ -202,11 +229,14 @@ static void capture_origin(sqt_oracle *o, ring_buf *b)
 {
 	const int S = o->p.nCSpatial, N = o->N;
 	const size_t row = 2 * NAX * (size_t)S;
+	if (o->p.flag_s) memcpy(b->org_sumVR, o->sumVR, sizeof(o->sumVR)); /* :1273-1275 */
 	if (o->p.flag_t) memcpy(b->org_pos, o->cur_xyz, sizeof(double) * 3 * (size_t)N);
+	if (o->p.flag_t && o->p.flag_M) memcpy(b->org_mu, o->cur_mu, sizeof(double) * 3 * (size_t)N);
 	if (o->p.flag_t && o->p.flag_V) memcpy(b->org_vel, o->cur_vel, sizeof(double) * 3 * (size_t)N);
 	if (o->p.flag_f) {
 		memcpy(b->org_rho, o->rho, sizeof(double) * row);
 		if (o->p.flag_V) memcpy(b->org_kvel, o->kvel, sizeof(double) * row);
+		if (o->p.flag_M) memcpy(b->org_kmu, o->kmu, sizeof(double) * row);
 		if (o->p.flag_F) {
 			memcpy(b->org_self, o->self, sizeof(double) * N * row);
 			memcpy(b->org_dist, o->dist, sizeof(double) * N * row);
@@ -220,12 +250,19 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 	const int S = o->p.nCSpatial, T = o->p.nCTime, N = o->N;
 	const int row = 2 * NAX * S;
 	/* InitTwoTimeCorr :1315-1367 (rrMSDCM is NOT zeroed: cumulative across buffer reuse) */
-	if (o->p.flag_t) { b->msd[lag] = 0.; b->mqd[lag] = 0.; if (o->p.flag_V) { b->cvv[lag] = 0.; b->cvcm[lag] = 0.; } }
+	if (o->p.flag_t) {
+		b->msd[lag] = 0.; b->mqd[lag] = 0.;
+		if (o->p.flag_V) { b->cvv[lag] = 0.; b->cvcm[lag] = 0.; }
+		if (o->p.flag_M) b->cmm[lag] = 0.;
+		if (o->p.flag_s) { for (int j = 0; j < 3; j++) b->msr1[3 * lag + j] = 0.; for (int j = 0; j < 9; j++) b->msr2[9 * lag + j] = 0.; }
+	}
 	if (o->p.flag_f) {
 		for (int nr = 0; nr < S; nr++) b->hist[nr * T + lag] = 0;
 		for (int k = 0; k < S; k++) {
 			b->F[k * T + lag] = 0.;
 			if (o->p.flag_V) { b->Cvrho[k * T + lag] = 0.; b->Crhov[k * T + lag] = 0.; b->Cvv2[k * T + lag] = 0.; }
+			if (o->p.flag_V && o->p.flag_M) { b->Cvmu[k * T + lag] = 0.; b->Cmuv[k * T + lag] = 0.; }
+			if (o->p.flag_M) { b->Cmurho[k * T + lag] = 0.; b->Crhomu[k * T + lag] = 0.; b->Cmumu[k * T + lag] = 0.; }
 			if (o->p.flag_F) { b->Fs[k * T + lag] = 0.; b->Fd[k * T + lag] = 0.; }
 		}
 	}
@@ -247,6 +284,13 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 				Cvv += vi[1] * vj[1];
 				Cvv += vi[2] * vj[2];
 			}
+			double Cmm = 0;
+			if (o->p.flag_M) { /* :1417-1421 */
+				const double *mi = o->cur_mu + 3 * (size_t)n, *mj = b->org_mu + 3 * (size_t)n;
+				Cmm = mi[0] * mj[0];
+				Cmm += mi[1] * mj[1];
+				Cmm += mi[2] * mj[2];
+			}
 			double dx = ri[0] - rj[0], dy = ri[1] - rj[1], dz = ri[2] - rj[2];
 			double dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;
 			double dr2 = dx2 + dy2 + dz2;
@@ -255,8 +299,10 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 				if (i_Dr < S) b->hist[i_Dr * T + lag]++;
 			}
 			b->msd[lag] += dr2;
+			b->msr1[3 * lag + 0] += dx2; b->msr1[3 * lag + 1] += dy2; b->msr1[3 * lag + 2] += dz2; /* :1434-1436, whatever the flags */
 			b->mqd[lag] += dr2 * dr2;
 			if (o->p.flag_V) b->cvv[lag] += Cvv;
+			if (o->p.flag_M) b->cmm[lag] += Cmm;
 		}
 		double dcm = (six - sjx) * (six - sjx);
 		dcm += (siy - sjy) * (siy - sjy);
@@ -269,6 +315,12 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 			b->cvcm[lag] += c / (N * N);
 		}
 	}
+	/* EvalTwoTimeCollective :1461-1476 */
+	if (o->p.flag_s)
+		for (int j = 0; j < 9; j++) {
+			const double d = o->sumVR[j] - b->org_sumVR[j];
+			b->msr2[9 * lag + j] += d * d;
+		}
 	/* EvalTwoTimeKSpace :1477-1591, w = 1 */
 	if (o->p.flag_f) {
 		const double w = 1.;
@@ -289,6 +341,15 @@ static void two_time(sqt_oracle *o, ring_buf *b, int lag)
 					b->Cvv2[nk * T + lag] += w * (o->kvel[mR] * b->org_kvel[mR] + o->kvel[mI] * b->org_kvel[mI]);
 					b->Crhov[nk * T + lag] += w * (o->kvel[mR] * b->org_rho[mR] + o->kvel[mI] * b->org_rho[mI]);
 					b->Cvrho[nk * T + lag] += w * (o->rho[mR] * b->org_kvel[mR] + o->rho[mI] * b->org_kvel[mI]);
+				}
+				if (o->p.flag_V && o->p.flag_M) { /* :1556-1564 */
+					b->Cmuv[nk * T + lag] += w * (o->kvel[mR] * b->org_kmu[mR] + o->kvel[mI] * b->org_kmu[mI]);
+					b->Cvmu[nk * T + lag] += w * (o->kmu[mR] * b->org_kvel[mR] + o->kmu[mI] * b->org_kvel[mI]);
+				}
+				if (o->p.flag_M) { /* :1565-1576 */
+					b->Crhomu[nk * T + lag] += w * (o->kmu[mR] * b->org_rho[mR] + o->kmu[mI] * b->org_rho[mI]);
+					b->Cmurho[nk * T + lag] += w * (o->rho[mR] * b->org_kmu[mR] + o->rho[mI] * b->org_kmu[mI]);
+					b->Cmumu[nk * T + lag] += w * (o->kmu[mR] * b->org_kmu[mR] + o->kmu[mI] * b->org_kmu[mI]);
 				}
 			}
 		}
@@ -320,6 +381,8 @@ static void print_process(sqt_oracle *o)
 					o->out2d[8][e] *= inverseNptls * average_number;
 					o->out2d[9][e] *= inverseNptls * average_number;
 				}
+				if (o->p.flag_V && o->p.flag_M) { o->out2d[11][e] *= inverseNptls * average_number; o->out2d[10][e] *= inverseNptls * average_number; } /* :614-617 */
+				if (o->p.flag_M) for (int q = 12; q < 15; q++) o->out2d[q][e] *= inverseNptls * average_number; /* :618-622 */
 			}
 		for (int nt = 1; nt < T; nt++)
 			for (int nr = 0; nr < S; nr++) o->out2d[6][nr * T + nt] *= o->factorDr[nr];
@@ -328,12 +391,21 @@ static void print_process(sqt_oracle *o)
 	double factor_msdcm = 1. / (o->countCorrAv);
 	double factor_Cvv = 1. / (N * o->countCorrAv * 3.);   /* :640-642 */
 	double factor_Cvcmvcm = 1. / (o->countCorrAv * 3.);
+	double scale_4stress = .5 * o->p.mass * o->p.mass / (o->countCorrAv * o->vol); /* :637 */
 	if (o->p.flag_t)
 		for (int nt = 0; nt < T; nt++) {
 			o->out1d[0][nt] *= scale_factor;
 			o->out1d[2][nt] *= factor_msdcm;
 			o->out1d[1][nt] *= scale_factor;
 			if (o->p.flag_V) { o->out1d[3][nt] *= factor_Cvv; o->out1d[4][nt] *= factor_Cvcmvcm; }
+			if (o->p.flag_s) { /* :660-670 */
+				for (int j = 0; j < 3; j++) o->out1d[6 + j][nt] = scale_factor * o->out1d[6 + j][nt];
+				for (int j = 0; j < 9; j++) o->out1d[9 + j][nt] = scale_4stress * o->out1d[9 + j][nt];
+				double r2[9]; /* xx xy xz yx yy yz zx zy zz; common.c:161-172 */
+				for (int j = 0; j < 9; j++) r2[j] = o->out1d[9 + j][nt];
+				o->out1d[18][nt] = (r2[0] + r2[4] + r2[8]) / 3.0;
+				o->out1d[19][nt] = (r2[1] + r2[2] + r2[3] + r2[5] + r2[6] + r2[7]) / 6.0;
+			}
 		}
 	o->n_print++;
 	o->printed_count = o->countCorrAv;
@@ -368,6 +440,8 @@ static int accumulate(sqt_oracle *o)
 						o->sum2d[8][e] += b->Crhov[e];
 						o->sum2d[9][e] += b->Cvv2[e];
 					}
+					if (o->p.flag_V && o->p.flag_M) { o->sum2d[10][e] += b->Cvmu[e]; o->sum2d[11][e] += b->Cmuv[e]; } /* :399-402 */
+					if (o->p.flag_M) { o->sum2d[12][e] += b->Cmurho[e]; o->sum2d[13][e] += b->Crhomu[e]; o->sum2d[14][e] += b->Cmumu[e]; } /* :403-407 */
 				}
 			for (int nt = 0; nt < T; nt++)
 				for (int nr = 0; nr < S; nr++) o->sum2d[6][nr * T + nt] += b->hist[nr * T + nt];
@@ -378,6 +452,11 @@ static int accumulate(sqt_oracle *o)
 				o->sum1d[2][nt] += b->msdcm[nt];
 				o->sum1d[1][nt] += b->mqd[nt];
 				if (o->p.flag_V) { o->sum1d[3][nt] += b->cvv[nt]; o->sum1d[4][nt] += b->cvcm[nt]; } /* :423-426 */
+				/* rrCmm is NOT accumulated (no rrCmmAv line in :420-432): sum1d[5] stays 0 */
+				if (o->p.flag_s) { /* :427-432 */
+					for (int j = 0; j < 3; j++) o->sum1d[6 + j][nt] += b->msr1[3 * nt + j];
+					for (int j = 0; j < 9; j++) o->sum1d[9 + j][nt] += b->msr2[9 * nt + j];
+				}
 			}
 		b->count = 0;
 		++o->countCorrAv;
@@ -394,7 +473,23 @@ int sqt_oracle_push_frame(sqt_oracle *o, const double *xyz, int n, double xlo, d
 
 int sqt_oracle_push_frame_v(sqt_oracle *o, const double *xyz, const double *vel, int n, double xlo, double xhi)
 {
-	if (o->p.flag_V && !vel) return -2;
+	return sqt_oracle_push_frame_vm(o, xyz, vel, NULL, n, xlo, xhi);
+}
+
+/* EvalOneTimeSumVR, lmp2sqt.c:1122-1142 */
+static void one_time_sum_vr(sqt_oracle *o)
+{
+	for (int n = 0; n < o->N; n++) {
+		const double *r = o->cur_xyz + 3 * (size_t)n, *v = o->cur_vel + 3 * (size_t)n;
+		for (int a = 0; a < 3; a++)
+			for (int b = 0; b < 3; b++) o->sumVR[3 * a + b] = o->sumVR[3 * a + b] + v[a] * r[b];
+	}
+}
+
+int sqt_oracle_push_frame_vm(sqt_oracle *o, const double *xyz, const double *vel, const double *mu, int n, double xlo, double xhi)
+{
+	if ((o->p.flag_V || o->p.flag_s) && !vel) return -2;
+	if (o->p.flag_M && !mu) return -2;
 	if (o->nSkip < o->p.nCSkip) { o->nSkip++; return 0; }
 	o->L = xhi - xlo;
 	o->vol = o->L * o->L * o->L;
@@ -403,7 +498,9 @@ int sqt_oracle_push_frame_v(sqt_oracle *o, const double *xyz, const double *vel,
 	o->kVal = 2. * M_PI / o->L;
 	o->cur_xyz = xyz;
 	o->cur_vel = vel;
+	o->cur_mu = mu;
 	if (o->p.flag_f) one_time_kspace(o);
+	if (o->p.flag_s) one_time_sum_vr(o); /* EvalOneTimeCorr :1250-1257 */
 	for (int nb = 0; nb < o->p.nCBuffer; nb++) {
 		ring_buf *b = &o->buf[nb];
 		if (b->count == 0) capture_origin(o, b);
@@ -414,6 +511,7 @@ int sqt_oracle_push_frame_v(sqt_oracle *o, const double *xyz, const double *vel,
 	o->nSkip = 0;
 	o->cur_xyz = NULL;
 	o->cur_vel = NULL;
+	o->cur_mu = NULL;
 	return printed;
 }
 

@@ -57,6 +57,14 @@ CASES = {
 # code and engine do not implement -V yet, only oracle/sqt_oracle.c does; tests/test_oracle.py pins it on this case.
 CASES_V = {
     "v1_velocity": dict(traj=[dict(n_cells=2, n_frames=40, seed=9, box_jitter=0.005)], S=5, T=8, B=4, skip=None, limit=14825, flags="FtV"),
+    # -M on a dump that carries mux muy muz (the reader normalises them, snapshot.c:440-459): C2_mu_mu / C2_mu_rho / C2_rho_mu
+    # files and the (always zero) Cmm column of the Dt file
+    "m1_magnet": dict(traj=[dict(n_cells=2, n_frames=40, seed=13, box_jitter=0.005)], S=5, T=8, B=4, skip=None, limit=14825, flags="FtM"),
+    # -s on a dump that carries vx vy vz: Stress file, msdx msdy msdz columns; with -F (sum_n v (x) r zeroed per frame) and
+    # alone (-s switches -t on; without -f the reference never zeroes sumVR_ct, so it keeps growing from frame to frame)
+    "s1_stress": dict(traj=[dict(n_cells=2, n_frames=40, seed=14, box_jitter=0.005)], S=5, T=8, B=4, skip=None, limit=14825, flags="Fts"),
+    # (zero_heap: without it the MSDCM column of this run's Dt file is uninitialised heap, rrMSDCM is never zeroed: lmp2sqt.c:1325-1333)
+    "s2_stress_alone": dict(traj=[dict(n_cells=2, n_frames=36, seed=15)], S=6, T=6, B=3, skip=1, limit=14825, flags="s", zero_heap=True),
 }
 
 
@@ -68,8 +76,9 @@ def main():
     for name, c in list(CASES.items()) + list(CASES_V.items()):
         if only and name not in only:
             continue
-        vel = "V" in c["flags"]
-        out = os.path.join(here, "velocity", name) if vel else os.path.join(here, name)
+        vel = "V" in c["flags"] or "s" in c["flags"]
+        dip = "M" in c["flags"]
+        out = os.path.join(here, "velocity", name) if (vel or dip) else os.path.join(here, name)
         shutil.rmtree(out, ignore_errors=True)
         os.makedirs(out)
         trajs = [synth.make_trajectory(**kw) for kw in c["traj"]]
@@ -77,13 +86,13 @@ def main():
             dumps = []
             for i, t in enumerate(trajs):
                 dn = "dump%d.lammpstrj" % i
-                synth.write_text_dump(t, os.path.join(td, dn), velocities=vel)
+                synth.write_text_dump(t, os.path.join(td, dn), velocities=vel, dipoles=dip)
                 dumps.append(dn)
             synth.write_deck(os.path.join(td, "in.lmp2sqt"), limitCorrAv=c["limit"], nCBuffer=c["B"],
                              nCSpatial=c["S"], nCTime=c["T"], nCSkip=c["skip"])
             shutil.copy(os.path.join(td, "in.lmp2sqt"), os.path.join(out, "in.lmp2sqt"))
-            cli_flags = {"Ft": ("-F", "-t"), "ft": ("-f", "-t"), "F": ("-F",), "t": ("-t",), "FtV": ("-F", "-t", "-V")}[c["flags"]]
-            r = pyoracle.run_reference_cli(td, "in.lmp2sqt", dumps, flags=cli_flags, threads=1)
+            cli_flags = tuple("-" + ch for ch in c["flags"])
+            r = pyoracle.run_reference_cli(td, "in.lmp2sqt", dumps, flags=cli_flags, threads=1, zero_heap=c.get("zero_heap", False))
             assert r.returncode == 0, r.stderr
             with open(os.path.join(out, "stdout.txt"), "w") as f:
                 f.write(r.stdout)
@@ -91,7 +100,8 @@ def main():
             for fn in ("output.binary", "output.txt", "output.log"):
                 if os.path.exists(os.path.join(td, fn)):
                     shutil.copy(os.path.join(td, fn), os.path.join(out, fn))
-            vel_files = (("C2_v_v000.info.*", "C2_v_v000.info"), ("C2_v_rho000.info.*", "C2_v_rho000.info"), ("C2_rho_v000.info.*", "C2_rho_v000.info")) if vel else ()
+            vel_files = tuple((n + "000.info.*", n + "000.info") for n in ("C2_v_v", "C2_v_rho", "C2_rho_v", "C2_mu_mu", "C2_mu_rho", "C2_rho_mu",
+                                                                            "C2_v_mu", "C2_mu_v", "Stress"))
             for pat, dst in (("SSF000.info.*", "SSF000.info"), ("Dt000.info.*", "Dt000.info")) + vel_files:
                 g = glob.glob(os.path.join(td, pat))
                 if g:

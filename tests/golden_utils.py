@@ -28,19 +28,25 @@ def read_dump_text(text: str) -> synth.Trajectory:
     """Minimal pure-Python reader of the LAMMPS text dump (test helper; the product reader is C)."""
     lines = text.split("\n")
     i = 0
-    pos, box, ts, vel = [], [], [], []
+    pos, box, ts, vel, mu = [], [], [], [], []
     while i < len(lines) and lines[i].startswith("ITEM: TIMESTEP"):
         ts.append(int(lines[i + 1]))
         n = int(lines[i + 3])
         b = [[float(v) for v in lines[i + 5 + a].split()[:2]] for a in range(3)]
+        cols = lines[i + 8].split()[2:]             # "ITEM: ATOMS id type xu yu zu [mux muy muz] [vx vy vz]"
         arr = np.loadtxt(io.StringIO("\n".join(lines[i + 9:i + 9 + n])), ndmin=2)
         pos.append(arr[:, 2:5])
-        if arr.shape[1] >= 8:                       # "id type xu yu zu vx vy vz"
-            vel.append(arr[:, 5:8])
+        if "mux" in cols:
+            mu.append(arr[:, cols.index("mux"):cols.index("mux") + 3])
+        if "vx" in cols:
+            vel.append(arr[:, cols.index("vx"):cols.index("vx") + 3])
         box.append(b)
         i += 9 + n
-    return synth.Trajectory(np.array(pos), np.array(box), np.array(ts), np.ones(pos[0].shape[0], dtype=np.int32),
-                            np.array(vel) if len(vel) == len(pos) else None)
+    t = synth.Trajectory(np.array(pos), np.array(box), np.array(ts), np.ones(pos[0].shape[0], dtype=np.int32),
+                         np.array(vel) if len(vel) == len(pos) else None)
+    if len(mu) == len(pos):
+        t._dipoles_raw = np.array(mu)              # Trajectory.dipoles normalises them like the reference's reader
+    return t
 
 
 def case_trajectories(name):

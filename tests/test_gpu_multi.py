@@ -68,7 +68,7 @@ def test_two_gpu_shards_match_single_gpu_and_oracle(tmp_path, S, T, B):
 # ---- G GPUs behind one caller thread (include/sqt.h sqt_multi_*, CLI -g N): SURVEY.md section 8e frame fan-out ------------
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("S,T,B,flags", [(6, 8, 4, "Ft"), (100, 6, 6, "Ft"), (30, 6, 6, "FtV"), (43, 6, 6, "Ft")])
+@pytest.mark.parametrize("S,T,B,flags", [(6, 8, 4, "Ft"), (100, 6, 6, "Ft"), (30, 6, 6, "FtV"), (43, 6, 6, "Ft"), (30, 6, 6, "FtVMs"), (70, 6, 6, "FtMs")])
 def test_in_process_fanout_matches_oracle_and_single_gpu(S, T, B, flags):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
@@ -84,6 +84,10 @@ def test_in_process_fanout_matches_oracle_and_single_gpu(S, T, B, flags):
     if "V" in flags:
         for k in ("avC2_v_rho", "avC2_rho_v", "avC2_v_v", "rrCvvAv", "rrCvcmvcmAv"):
             np.testing.assert_allclose(got[k], raw[k], rtol=1e-6, atol=1e-9 * np.abs(raw[k]).max(), err_msg=k)
+    if "M" in flags or "s" in flags:                  # the sums the shards exchange for -M / -s (kmu_q1, sum v (x) r, per-axis MSD)
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from test_gpu_fields import _check_fields
+        _check_fields(got, raw, flags, "fan-out x2 " + flags)
     single, e1 = run_trajectories([traj], deck, flags)
     s = single.to_dict()
     assert np.array_equal(got["avDrTable"], s["avDrTable"])

@@ -78,7 +78,7 @@ def test_velocity_nCSkip_two_files_and_midrun_flush():
 
 def test_velocity_requires_velocities_and_supported_nCSpatial():
     from lmp2sqt_b200 import SqtError
-    with pytest.raises(SqtError, match="-V needs nCSpatial"):
+    with pytest.raises(SqtError, match="-V / -M need nCSpatial"):
         SpacetimeCorr(Deck(limitCorrAv=BIG, nCBuffer=2, nCSpatial=300, nCTime=4), "FtV")
     eng = SpacetimeCorr(Deck(limitCorrAv=BIG, nCBuffer=2, nCSpatial=4, nCTime=4), "FtV")
     eng.InitSpacetimeCorr()

@@ -458,3 +458,95 @@ def test_integration_snippet_compiles_and_links(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 2                                 # usage path: the binary loads both libraries and starts
+
+
+# ---- -V / -M / -s files: C2_* tables, Stress file, extra Dt columns ----------------------------------
+def _results_from_x(raw: dict, S, T, flags) -> Results:
+    r = _results_from(raw, S, T)
+    n2, n1 = pyoracle.names_for(flags)
+    for _, k in n2[7:] + n1[3:]:
+        r.array(k)[...] = raw[k]
+    if "s" in flags:
+        for k in ("rrMSR1_R_Av", "rrMSR2_VR_Av"):
+            r.array(k)[...] = raw[k]
+    return r
+
+
+@pytest.mark.parametrize("name", ["v1_velocity", "m1_magnet", "s1_stress", "s2_stress_alone"])
+def test_writers_reproduce_reference_velocity_magnet_stress_files_byte_for_byte(name, tmp_path):
+    """PrintProcess with -V / -M / -s: every file the reference binary wrote for the fixture, byte for byte, from the raw sums
+    the oracle holds at the moment of the print (lmp2sqt.c:933-993 C2_* tables, :1006-1026 Stress, :1030-1076 Dt columns)."""
+    import gzip
+    import json
+    from golden_utils import GOLDEN, read_dump_text
+    g = os.path.join(GOLDEN, "velocity", name)
+    c = json.load(open(os.path.join(g, "case.json")))
+    with gzip.open(os.path.join(g, "dump0.lammpstrj.gz"), "rt") as f:
+        traj = read_dump_text(f.read())
+    S, T, flags = c["S"], c["T"], c["flags"]
+    printed, raw, log = pyoracle.run_port(None, S, T, c["B"], nCSkip=c["skip"] or 0, limitCorrAv=c["limit"], files=[traj], flags=flags)
+    res = _results_from_x(printed["_raw_at_print"], S, T, flags)
+    deck = Deck.read(os.path.join(g, "in.lmp2sqt"))
+    res.print_process(str(tmp_path), deck, flags, date="GOLD")
+    want = sorted(f for f in os.listdir(g) if f.endswith(".info") or f.startswith("output."))
+    assert len(want) >= 3
+    for fn in want:
+        ours = fn.replace(".info", ".info.GOLD") if fn.endswith(".info") else fn
+        assert (tmp_path / ours).exists(), fn
+        a, b = (tmp_path / ours).read_bytes(), open(os.path.join(g, fn), "rb").read()
+        if fn.startswith("Dt") and "s" not in flags:
+            assert dt_rows_without_uninitialised_columns(a.decode()) == dt_rows_without_uninitialised_columns(b.decode())
+        else:
+            assert a == b, fn
+    made = sorted(f.replace(".GOLD", "") for f in os.listdir(tmp_path))
+    assert made == want                                              # and nothing the reference does not write
+    got = res.to_dict()                                              # normalised in place like the reference's globals
+    if "s" in flags:
+        assert np.array_equal(got["rrMSR2_VR_Av"], printed["rrMSR2_VR_Av"]) and np.array_equal(got["rrMSR1_R_Av"], printed["rrMSR1_R_Av"])
+    if "M" in flags:
+        assert np.array_equal(got["avC2_mu_mu"], printed["avC2_mu_mu"])
+
+
+def test_mmap_reader_dipole_and_velocity_columns(tmp_path):
+    """-M: mux muy muz are normalised to unit vectors with the reference's own operation order (make_atom_dipole,
+    snapshot.c:440-459); the 11-column style yields both dipoles and velocities; asking a style for what it does not carry
+    fails the frame."""
+    t = synth.make_trajectory(n_cells=2, n_frames=3, seed=2)
+    h = _lib.host_lib()
+
+    def read(path, want_v, want_m):
+        r = h.sqt_reader_open(str(path).encode(), 2)
+        hd = SqtFrameHeader()
+        out = []
+        while h.sqt_reader_next_header(r, C.byref(hd)):
+            n = hd.n_atoms
+            a = np.full((9, n), np.nan)
+            p = [a[i].ctypes.data for i in range(9)]
+            ok = h.sqt_reader_read_atoms_vm(r, C.byref(hd), p[0], p[1], p[2], *(p[3:6] if want_v else [None] * 3), *(p[6:9] if want_m else [None] * 3))
+            if not ok:
+                break
+            out.append(a.copy())
+        h.sqt_reader_close(r)
+        return out
+
+    synth.write_text_dump(t, str(tmp_path / "mu"), dipoles=True)
+    synth.write_text_dump(t, str(tmp_path / "all"), dipoles=True, velocities=True)
+    synth.write_text_dump(t, str(tmp_path / "vel"), velocities=True)
+    fm = read(tmp_path / "mu", False, True)
+    assert len(fm) == 3
+    for f in range(3):
+        assert np.array_equal(fm[f][:3], t.positions[f].T)
+        assert np.array_equal(fm[f][6:9], t.dipoles[f].T)            # bit for bit: same sqrt, same divisions
+        np.testing.assert_allclose(np.linalg.norm(fm[f][6:9], axis=0), 1.0, rtol=1e-15)
+    fa = read(tmp_path / "all", True, True)
+    assert len(fa) == 3 and np.array_equal(fa[1][3:6], t.velocities[1].T) and np.array_equal(fa[1][6:9], t.dipoles[1].T)
+    assert np.array_equal(read(tmp_path / "all", False, True)[2][6:9], t.dipoles[2].T)   # the reference's own reading of this style
+    assert read(tmp_path / "all", True, False) == []                 # velocities alone: the 8-column velocity style only
+    assert read(tmp_path / "vel", False, True) == [] and read(tmp_path / "mu", True, True) == []
+    assert np.array_equal(read(tmp_path / "vel", True, False)[0][3:6], t.velocities[0].T)
+    (tmp_path / "tiny").write_text((tmp_path / "mu").read_text().replace(" mux muy muz\n1 1 ", " mux muy muz\n1 1 ", 1))
+    # a dipole shorter than 1e-3 is left unset by the reference; zero here
+    txt = (tmp_path / "mu").read_text().split("\n")
+    txt[9] = " ".join(txt[9].split()[:5] + ["0.000100", "0.000200", "0.000100"])
+    (tmp_path / "tiny").write_text("\n".join(txt))
+    assert not read(tmp_path / "tiny", False, True)[0][6:9, 0].any()

@@ -186,3 +186,81 @@ def test_port_bit_identical_to_live_reference_random_sweep(seed):
         assert np.array_equal(ref["raw"][k], raw[k]), k
         if raw["countCorrAv"] > 0:
             assert np.array_equal(ref["printed"][k], pr[k], equal_nan=True), k
+
+
+# ---- -M (flag_magnet) and -s (flag_s): SURVEY.md section 8f.4, the rest of the row ------------------------------------------
+FIELD_CASES = ["m1_magnet", "s1_stress", "s2_stress_alone"]
+
+
+def _extra_names(flags):
+    n2, n1 = pyoracle.names_for(flags)
+    names = [n for _, n in n2] + [n for _, n in n1]
+    if "s" in flags:
+        names += ["rrMSR1_R_Av", "rrMSR2_VR_Av"]
+    return names
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("flags", ["FtM", "FtVM", "Fts", "s", "ftMs", "FtVMs", "fM"])
+def test_port_magnet_and_stress_bit_identical_to_live_reference(flags):
+    """The restatement of -M (kmu_q1 lmp2sqt.c:1209-1214, C2_mu_mu / C2_rho_mu / C2_mu_rho :1565-1576, C2_v_mu / C2_mu_v
+    :1556-1564, rrCmm never accumulated :420-432) and of -s (sumVR_ct :1122-1142 -- zeroed under -f only, :1120 --, orgSumVR
+    :1273-1275, rrMSR1_R :1434-1436, rrMSR2_VR :1461-1476, scaling :660-669) against the unmodified reference on the same
+    frames, two input files."""
+    t1 = synth.make_trajectory(n_cells=2, n_frames=43, box_jitter=0.01, seed=505)
+    t2 = synth.make_trajectory(n_cells=2, n_frames=29, box_jitter=0.01, seed=606)
+    S, T, B = 6, 8, 4
+    ref = pyoracle.run_reference([t1, t2], S, T, B, limit=1000, flags=flags)
+    extra = sum((t.n_frames - T) // (T // B) for t in (t1, t2))
+    pr, raw, log = pyoracle.run_port(None, S, T, B, limitCorrAv=1000 - extra, files=[t1, t2], flags=flags)
+    assert ref["raw"]["countCorrAv"] == raw["countCorrAv"] > 0 and ref["log"] == [l[0] for l in log]
+    names = _extra_names(flags)
+    for k in names:
+        assert np.array_equal(ref["raw"][k], raw[k]), k
+        assert np.array_equal(ref["printed"][k], pr[k], equal_nan=True), k
+    if "s" in flags:
+        for k in ("rrMSR2_VR_Av_dig", "rrMSR2_VR_Av_offdig"):
+            assert np.array_equal(ref["printed"][k], pr[k]), k
+        assert np.abs(raw["rrMSR2_VR_Av"]).max() > 0 and np.abs(raw["rrMSR1_R_Av"]).max() > 0
+        np.testing.assert_allclose(raw["rrMSR1_R_Av"].sum(axis=1), raw["rrMSDAv"], rtol=1e-12)   # msdx + msdy + msdz = MSD
+    if "M" in flags:
+        assert np.abs(raw["avC2_mu_mu"]).max() > 0
+        assert not raw["rrCmmAv"].any()                      # the reference's quirk: printed, never summed
+
+
+@pytest.mark.parametrize("name", FIELD_CASES)
+def test_port_magnet_and_stress_reproduce_committed_reference_fixtures(name):
+    """The same against COMMITTED fixtures (tests/golden/velocity/: written by the unmodified reference CLI with -F -t -M on a
+    dump that carries mux muy muz, and with -F -t -s / -s on one that carries vx vy vz, plus the raw fp64 sums read from its
+    globals), so that the check also runs where /root/reference does not exist."""
+    import gzip
+    import json
+    from golden_utils import GOLDEN, read_dump_text
+    d = os.path.join(GOLDEN, "velocity", name)
+    c = json.load(open(os.path.join(d, "case.json")))
+    a = dict(np.load(os.path.join(d, "arrays.npz")))
+    with gzip.open(os.path.join(d, "dump0.lammpstrj.gz"), "rt") as f:
+        traj = read_dump_text(f.read())
+    S, T, B, skip = c["S"], c["T"], c["B"], c["skip"] or 0
+    _, raw, log = pyoracle.run_port(None, S, T, B, nCSkip=skip, limitCorrAv=10**8, files=[traj], flags=c["flags"], finish=False)
+    assert raw["countCorrAv"] == int(a["raw_countCorrAv"]) and [l[0] for l in log] == list(a["count_log"])
+    for k in _extra_names(c["flags"]):
+        assert np.array_equal(raw[k], a["raw_" + k]), k
+    # what the reference binary printed
+    printed, _, _ = pyoracle.run_port(None, S, T, B, nCSkip=skip, limitCorrAv=c["limit"], files=[traj], flags=c["flags"])
+    rows = [ln.split() for ln in open(os.path.join(d, "Dt000.info")).read().strip().split("\n")[1:]]
+    if "s" in c["flags"]:
+        for nt, r in enumerate(rows):
+            assert r[2:5] == [("%8.4g" % printed["rrMSR1_R_Av"][nt, j]).strip() for j in range(3)], nt
+        tab = [ln.split() for ln in open(os.path.join(d, "Stress000.info")).read().strip().split("\n")[1:]]
+        assert len(tab) == T
+        for nt, r in enumerate(tab):
+            m = printed["rrMSR2_VR_Av"][nt]
+            want = [printed["rrMSR2_VR_Av_dig"][nt], printed["rrMSR2_VR_Av_offdig"][nt], m[1], m[3], m[7], m[5], m[2], m[6]]
+            assert r[1:] == [("%8.4g" % v).strip() for v in want], nt
+    if "M" in c["flags"]:
+        assert all(r[8] == "0.0000" for r in rows)               # the Cmm column
+        for fn, key in (("C2_mu_mu000.info", "avC2_mu_mu"), ("C2_rho_mu000.info", "avC2_rho_mu"), ("C2_mu_rho000.info", "avC2_mu_rho")):
+            tab = [ln.split() for ln in open(os.path.join(d, fn)).read().strip().split("\n")]
+            for nt, r in enumerate(tab):
+                assert r[1:] == [("%8.4e" % printed[key][nk, nt]).strip() for nk in range(S)], (fn, nt)
