@@ -57,7 +57,10 @@ typedef struct {
 	int flag_M;          /* -M (flag_magnet, :177): dipole-weighted density kmu_q1 and its correlators; frames then carry mux muy muz */
 	int flag_s;          /* -s (flag_s, :156-160; switches flag_t on like getopt does): per-axis MSD and the stress-like
 	                      * squared change of sum_n v (x) r; frames then carry vx vy vz */
-	int reserved[3];     /* must be zero */
+	int n_types;         /* per-type partials (not in the reference): > 1 = atoms carry a species 1 .. n_types
+	                      * (the dump's `type` column, sqt_set_types) and F_ab(q,t), F_s,a(q,t), MSD_a, MQD_a and the van Hove table of
+	                      * every species are accumulated beside the totals.  0 / 1 = off.  Not with -V / -M / -s */
+	int reserved[2];     /* must be zero */
 } sqt_params;
 
 /* Largest nCSpatial the kernels cover (the reference accepts any; a deck beyond this is refused by sqt_create).  With
@@ -94,9 +97,19 @@ typedef struct {
 	/* -s only: rrMSR1_R_Av [nCTime][3] (x y z) and rrMSR2_VR_Av [nCTime][9] (xx xy xz yx yy yz zx zy zz), the reference's
 	 * VecR3 / Rank2R3 arrays (:427-432) */
 	double *rrMSR1_R_Av, *rrMSR2_VR_Av;
+	/* per-type partials (sqt_results_alloc_types; NULL / 0 otherwise), raw sums like the arrays above:
+	 *   avF_ab [a][b][nCSpatial][nCTime]   sum over buffers and axes of Re[rho_a(q,t) rho_b*(q,t0)]       (sum over a, b = avF_qq2)
+	 *   avF_s_a [a][nCSpatial][nCTime]     the self part restricted to species a                          (sum over a = avF_s_qq2)
+	 *   avDrTable_a [a][nCSpatial][nCTime] van Hove counts of species a                                   (sum over a = avDrTable)
+	 *   rrMSD_a, rrMQD_a [a][nCTime]       sum over the atoms of species a                                (sum over a = rrMSDAv, rrMQDAv)
+	 *   nPtls_a [a]                        atoms of species a over all shards */
+	int n_types;
+	long long nPtls_a[8];
+	double *avF_ab, *avF_s_a, *avDrTable_a, *rrMSD_a, *rrMQD_a;
 } sqt_results;
 
 int  sqt_results_alloc(sqt_results *r, int nCSpatial, int nCTime);
+int  sqt_results_alloc_types(sqt_results *r, int n_types);   /* after sqt_results_alloc: the per-type arrays */
 void sqt_results_free(sqt_results *r);
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -111,6 +124,10 @@ int  sqt_set_limit(sqt_handle *h, int limitCorrAv);
 /* InitSpacetimeCorr (lmp2sqt.c:446-475): count[nb] = -nb*nCTime/nCBuffer, nSkip = 0.  Once per
  * input file; the averages persist across files, partially filled buffers are discarded. */
 int  sqt_begin_file(sqt_handle *h);
+
+/* Per-type partials (sqt_params.n_types > 1): the species (1 .. n_types) of this handle's atoms in dump order, once, before
+ * the first frame.  Atoms keep their line order from frame to frame (snapshot.c:357-368), so the species never change. */
+int  sqt_set_types(sqt_handle *h, const int *types, int n_atoms_local);
 
 /* ---- frames ------------------------------------------------------------------------------ */
 /* Pinned host staging for the next frame, SoA: x[0..n), y[0..n), z[0..n) as doubles
@@ -206,6 +223,7 @@ const char *sqt_multi_last_error(const sqt_multi *m);
 int  sqt_multi_n_gpus(const sqt_multi *m);
 sqt_handle *sqt_multi_handle(sqt_multi *m, int rank);      /* introspection only */
 int  sqt_multi_set_limit(sqt_multi *m, int limitCorrAv);
+int  sqt_multi_set_types(sqt_multi *m, const int *types, int n_atoms);   /* per-type partials: species of ALL atoms, dump order */
 int  sqt_multi_begin_file(sqt_multi *m);
 /* pinned (portable) SoA for a whole frame: x[n] y[n] z[n] (+ vx[n] vy[n] vz[n] with flag_V / flag_s, + mux[n] muy[n] muz[n] with
  * flag_M); double buffered */

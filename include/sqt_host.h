@@ -82,6 +82,9 @@ int sqt_reader_read_atoms_v(sqt_reader *r, const sqt_frame_header *hd, double *x
 int sqt_reader_read_atoms_vm(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z, double *vx, double *vy, double *vz,
                              double *mux, double *muy, double *muz);
 int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd);
+/* Per-type partials: the `type` column of the atom block at the read position (text dumps; the position is not advanced).
+ * 1 ok / 0 not available. */
+int sqt_reader_peek_types(sqt_reader *r, const sqt_frame_header *hd, int *types);
 
 /* factorDr[nr], lmp2sqt.c:1987-2009, from what the engine recorded at the first processed frame. */
 void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr);
@@ -99,6 +102,12 @@ typedef struct { int f, F, t, V, M, s; } sqt_flags;
  * column of the Dt file, with -s the Stress%03d.info.<date> file and the msdx msdy msdz columns (lmp2sqt.c:933-1076). */
 void sqt_host_normalise_x(sqt_results *r, const sqt_deck *d, const sqt_flags *fl);
 int sqt_host_print_process_x(const char *dir, sqt_results *r, const sqt_deck *d, const sqt_flags *fl, const char *date);
+/* Per-type partials (sqt_results.n_types > 1; an extension, the reference has no per-type code).  Normalisation, in place:
+ *   F_ab *= 1 / (N 3 cnt)   (so that sum_ab F_ab = F(q,t) of output.txt),   F_s,a *= 1 / (N_a 3 cnt)   (F_s,a(q,0) = 1),
+ *   MSD_a, MQD_a *= 1 / (N_a cnt),   van Hove_a[lag >= 1] *= factorDr N / N_a.
+ * sqt_host_print_types writes them as text blocks into `types%03d.info.<date>` beside the Dt / SSF files (same index rule). */
+void sqt_host_normalise_types(sqt_results *r, const sqt_deck *d);
+int sqt_host_print_types(const char *dir, sqt_results *r, const sqt_deck *d, const sqt_flags *fl, const char *date);
 /* The same with -V: also normalises the current correlators and writes C2_v_v / C2_v_rho / C2_rho_v%03d.info.<date> and the
  * Cvv, Cvcmvcm columns of the Dt file (lmp2sqt.c:933-993, 1033-1076). */
 int sqt_host_print_process_v(const char *dir, sqt_results *r, const sqt_deck *d, int flag_f, int flag_F, int flag_t, int flag_V,

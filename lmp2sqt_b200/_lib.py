@@ -24,7 +24,7 @@ class SqtParams(C.Structure):
                 ("limitCorrAv", C.c_int), ("nCBuffer", C.c_int), ("nCSpatial", C.c_int), ("nCTime", C.c_int),
                 ("nCSkip", C.c_int), ("flag_f", C.c_int), ("flag_F", C.c_int), ("flag_t", C.c_int),
                 ("device", C.c_int), ("n_gpus", C.c_int), ("flag_V", C.c_int), ("flag_M", C.c_int), ("flag_s", C.c_int),
-                ("reserved", C.c_int * 3)]
+                ("n_types", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class SqtFlags(C.Structure):
@@ -43,7 +43,9 @@ class SqtResults(C.Structure):
                 ("rrMSDAv", _PD), ("rrMQDAv", _PD), ("rrMSDCMAv", _PD),
                 ("avC2_v_rho", _PD), ("avC2_rho_v", _PD), ("avC2_v_v", _PD), ("rrCvvAv", _PD), ("rrCvcmvcmAv", _PD),
                 ("avC2_v_mu", _PD), ("avC2_mu_v", _PD), ("avC2_mu_rho", _PD), ("avC2_rho_mu", _PD), ("avC2_mu_mu", _PD),
-                ("rrCmmAv", _PD), ("rrMSR1_R_Av", _PD), ("rrMSR2_VR_Av", _PD)]
+                ("rrCmmAv", _PD), ("rrMSR1_R_Av", _PD), ("rrMSR2_VR_Av", _PD),
+                ("n_types", C.c_int), ("nPtls_a", C.c_longlong * 8),
+                ("avF_ab", _PD), ("avF_s_a", _PD), ("avDrTable_a", _PD), ("rrMSD_a", _PD), ("rrMQD_a", _PD)]
 
 
 class SqtDeck(C.Structure):
@@ -70,7 +72,10 @@ class SqtAnalysis(C.Structure):
 # every symbol include/sqt.h declares: (name, restype, argtypes)
 ENGINE_API = [
     ("sqt_results_alloc", C.c_int, [C.POINTER(SqtResults), C.c_int, C.c_int]),
+    ("sqt_results_alloc_types", C.c_int, [C.POINTER(SqtResults), C.c_int]),
     ("sqt_results_free", None, [C.POINTER(SqtResults)]),
+    ("sqt_set_types", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("sqt_multi_set_types", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("sqt_create", C.c_int, [C.POINTER(SqtParams), C.POINTER(C.c_void_p)]),
     ("sqt_destroy", None, [C.c_void_p]),
     ("sqt_last_error", C.c_char_p, [C.c_void_p]),
@@ -147,6 +152,9 @@ HOST_API = [
     ("sqt_host_print_process_v", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),
     ("sqt_host_normalise_x", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck), C.POINTER(SqtFlags)]),
     ("sqt_host_print_process_x", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.POINTER(SqtFlags), C.c_char_p]),
+    ("sqt_host_normalise_types", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck)]),
+    ("sqt_host_print_types", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.POINTER(SqtFlags), C.c_char_p]),
+    ("sqt_reader_peek_types", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p]),
     ("sqt_analysis_load", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p, C.c_char_p, C.c_int]),
     ("sqt_analysis_from_results", C.c_int, [C.POINTER(SqtAnalysis), C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int]),
     ("sqt_analysis_time", C.c_int, [C.POINTER(SqtAnalysis), C.c_int, C.c_double, C.c_char_p]),

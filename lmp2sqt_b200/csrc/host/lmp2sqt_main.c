@@ -10,6 +10,8 @@
  * (snapshot.c:263-331); asking for both reads the 11-column style in full, which the reference's reader never does
  * (its 11-column branch is shadowed by the 8-column dipole test, :262 vs :308).
  *
+ * Extension: `-T n` accumulates the per-type partials F_ab(q,t), F_s,a(q,t), MSD_a and the van Hove table of the n species the
+ * dump's `type` column names (written to types%03d.info.<date>; everything else is unchanged).
  * Extension: `-g N` (or SQT_GPUS=N) shards every frame by particle over N GPUs of this box (devices SQT_DEVICE ..
  * SQT_DEVICE + N - 1): one reader thread, one pinned frame, N asynchronous chunk copies.
  */
@@ -38,7 +40,7 @@ int main(int argc, char **argv)
 {
 	bool flag_f = false, flag_F = false, flag_t = false, flag_d = false, flag_V = false, flag_M = false, flag_s = false;
 	char inputFilename[512] = "in.lmp2sqt"; /* lmp2sqt.c:108 */
-	int device = 0, n_gpus = 1;
+	int device = 0, n_gpus = 1, n_types = 0;
 	const char *dev_env = getenv("SQT_DEVICE");
 	if (dev_env && *dev_env) device = atoi(dev_env);
 	const char *gpus_env = getenv("SQT_GPUS");
@@ -57,11 +59,12 @@ int main(int argc, char **argv)
 	         "		-M) magnet correlation \n"
 	         "		-d) Get Amount of dynamic memory allocation \n"
 	         "   -i) argment filename for input variable \n"
-	         "   -g) number of GPUs of this box to shard the particles over   [B200 build only; default 1 or $SQT_GPUS]\n",
+	         "   -g) number of GPUs of this box to shard the particles over   [B200 build only; default 1 or $SQT_GPUS]\n"
+	         "   -T) number of species (dump column `type` = 1..n): per-type partials F_ab, F_s,a, MSD_a   [B200 build only]\n",
 	         argv[0]);
 	if (argc < 2) { puts(help_message); return EXIT_FAILURE; }
 	for (;;) {
-		int opt = getopt(argc, argv, "tfFsVMi:dg:");
+		int opt = getopt(argc, argv, "tfFsVMi:dg:T:");
 		if (opt == -1) break;
 		switch (opt) {
 		case 't': puts("flag_t on : two time correlation"); flag_t = true; break;
@@ -78,6 +81,7 @@ int main(int argc, char **argv)
 			break;
 		case 'V': puts("flag_velocity on : velocity correlation on"); flag_V = true; break; /* lmp2sqt.c:171-173 */
 		case 'g': n_gpus = atoi(optarg); break;
+		case 'T': n_types = atoi(optarg); break;
 		case 's': /* lmp2sqt.c:156-160 */
 			puts("flag_s on : stress tensor calculation on");
 			puts("require flag_t : also on");
@@ -146,7 +150,7 @@ int main(int argc, char **argv)
 	prm.kVal = deck.kVal; prm.deltaT = deck.deltaT; prm.mass = deck.mass; prm.rVal = deck.rVal;
 	prm.limitCorrAv = limitCorrAv; prm.nCBuffer = deck.nCBuffer; prm.nCSpatial = deck.nCSpatial; prm.nCTime = deck.nCTime;
 	prm.nCSkip = deck.nCSkip; prm.flag_f = flag_f; prm.flag_F = flag_F; prm.flag_t = flag_t; prm.device = device;
-	prm.n_gpus = n_gpus; prm.flag_V = flag_V; prm.flag_M = flag_M; prm.flag_s = flag_s;
+	prm.n_gpus = n_gpus; prm.flag_V = flag_V; prm.flag_M = flag_M; prm.flag_s = flag_s; prm.n_types = n_types > 1 ? n_types : 0;
 	const sqt_flags fl = { flag_f, flag_F, flag_t, flag_V, flag_M, flag_s };
 	const bool want_v = flag_V || flag_s, want_m = flag_M;
 	if (deck.nCBuffer > deck.nCTime) { fputs("Error nCBuffer> nCTime\n", stderr); exit(1); }
@@ -184,6 +188,8 @@ int main(int argc, char **argv)
 	if (rc) die_engine(NULL, "sqt_multi_create", rc);
 	sqt_results res;
 	if (sqt_results_alloc(&res, deck.nCSpatial, deck.nCTime)) { fputs("Reserving memory Error!!!!!!\n", stdout); exit(1); }
+	if (n_types > 1 && sqt_results_alloc_types(&res, n_types)) { fputs("Reserving memory Error!!!!!!\n", stdout); exit(1); }
+	bool types_set = n_types <= 1;
 
 	int full_n_snaps_index = 0, progress = -1;
 	double kVal = deck.kVal;
@@ -206,6 +212,14 @@ int main(int argc, char **argv)
 		fprintf(stderr, "FULL_SNAPS = %5d\n", full_n_snaps);
 		for (long ns = 0; ns < num_data[a]; ns++) {
 			if (!sqt_reader_next_header(rd, &hd)) break;
+			if (!types_set) { /* species from the first frame that is read: line order is fixed for the whole run */
+				int *types = (int *)malloc(sizeof(int) * (size_t)(hd.n_atoms > 0 ? hd.n_atoms : 1));
+				if (!sqt_reader_peek_types(rd, &hd, types)) { fprintf(stderr, "-T needs a text dump with a `type` column (file %s)\n", argv[a]); exit(1); }
+				rc = sqt_multi_set_types(h, types, hd.n_atoms);
+				if (rc) die_engine(h, "sqt_set_types", rc);
+				free(types);
+				types_set = true;
+			}
 			double *stage = sqt_multi_stage_acquire(h, hd.n_atoms);
 			if (!stage) die_engine(h, "sqt_stage_acquire", -1);
 			const size_t na = (size_t)hd.n_atoms;
@@ -226,7 +240,7 @@ int main(int argc, char **argv)
 			if (rc == SQT_FLUSH) { /* PrintProcess from AccumSpacetimeCorr, :438-440 */
 				rc = sqt_multi_fetch_results(h, &res);
 				if (rc) die_engine(h, "sqt_fetch_results", rc);
-				if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
+				if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL) || sqt_host_print_types(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
 			}
 			full_n_snaps_index++;
 			int new_progress = (int)(10000.0 * full_n_snaps_index / full_n_snaps);
@@ -243,7 +257,7 @@ int main(int argc, char **argv)
 	if (rc < 0) die_engine(h, "sqt_finish", rc);
 	if (rc == 1) { /* lmp2sqt.c:327-333 */
 		fprintf(stderr, "limit corr  = %d, countCorrAv = %d\n", limitCorrAv, res.countCorrAv);
-		if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
+		if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL) || sqt_host_print_types(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
 	}
 	fprintf(stderr, "engine: %d GPU%s; %s; %lld kernel launches\n", sqt_multi_n_gpus(h), sqt_multi_n_gpus(h) > 1 ? "s, particle-sharded" : "",
 	        sqt_kernel_config(sqt_multi_handle(h, 0)), sqt_multi_kernel_launches(h));

@@ -530,6 +530,23 @@ int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd)
 	return 1;
 }
 
+/* the `type` column (atoi of the second token, snapshot.c:362) of the atom block at the read position, which stays where it is */
+int sqt_reader_peek_types(sqt_reader *r, const sqt_frame_header *hd, int *types)
+{
+	if (r->raw != 0 || hd->n_atoms <= 0) return 0; /* text dumps only: the binary frame files carry no species */
+	size_t pos = r->pos;
+	for (int i = 0; i < hd->n_atoms; i++) {
+		const char *p, *e;
+		if (!take_line(r, &pos, &p, &e)) return 0;
+		const char *c = p;
+		if (!tok_skip(&c, e)) return 0;
+		while (c < e && *c == ' ') c++;
+		if (c >= e) return 0;
+		types[i] = atoi(c);
+	}
+	return 1;
+}
+
 int sqt_reader_read_atoms(sqt_reader *r, const sqt_frame_header *hd, double *x, double *y, double *z)
 {
 	return sqt_reader_read_atoms_v(r, hd, x, y, z, NULL, NULL, NULL);

@@ -114,6 +114,29 @@ void sqt_host_normalise_x(sqt_results *r, const sqt_deck *d, const sqt_flags *fl
 	}
 }
 
+void sqt_host_normalise_types(sqt_results *r, const sqt_deck *d)
+{
+	const int nt = r->n_types, S = r->nCSpatial, T = r->nCTime;
+	if (nt < 2 || !r->avF_ab) return;
+	const double N = (double)r->nPtls, cnt = (double)r->countCorrAv;
+	const size_t ST = (size_t)S * T;
+	for (size_t e = 0; e < (size_t)nt * nt * ST; e++) r->avF_ab[e] = (r->avF_ab[e] * (1. / N)) * (1. / (3.0 * cnt));
+	double *factorDr = (double *)malloc(sizeof(double) * S);
+	sqt_host_factor_dr(r, d->rVal, factorDr);
+	for (int a = 0; a < nt; a++) {
+		const double Na = (double)r->nPtls_a[a];
+		if (Na <= 0) continue; /* an empty species: all sums are zero already */
+		for (size_t e = 0; e < ST; e++) r->avF_s_a[a * ST + e] = (r->avF_s_a[a * ST + e] * (1. / Na)) * (1. / (3.0 * cnt));
+		for (int nr = 0; nr < S; nr++)
+			for (int lag = 1; lag < T; lag++) r->avDrTable_a[a * ST + (size_t)nr * T + lag] *= factorDr[nr] * (N / Na);
+		for (int lag = 0; lag < T; lag++) {
+			r->rrMSD_a[a * T + lag] *= 1. / (Na * cnt);
+			r->rrMQD_a[a * T + lag] *= 1. / (Na * cnt);
+		}
+	}
+	free(factorDr);
+}
+
 static void join(char *out, size_t n, const char *dir, const char *name)
 {
 	if (dir && *dir) snprintf(out, n, "%s/%s", dir, name);
@@ -262,6 +285,74 @@ static int write_etc(const char *dir, const sqt_results *r, const sqt_deck *d, c
 		free(rrDt);
 		fclose(fp);
 	}
+	return 0;
+}
+
+int sqt_host_print_types(const char *dir, sqt_results *r, const sqt_deck *d, const sqt_flags *fl, const char *date)
+{
+	const int nt = r->n_types, S = r->nCSpatial, T = r->nCTime;
+	if (nt < 2 || !r->avF_ab) return 0;
+	const int flag_f = fl->f || fl->F, flag_F = fl->F, flag_t = fl->t || fl->s;
+	char today[32], name[64], path[512];
+	if (!date) {
+		time_t raw = time(NULL);
+		strftime(today, sizeof(today), "%y%m%d", localtime(&raw));
+		date = today;
+	}
+	int nfile = 0;
+	do {
+		snprintf(name, sizeof(name), "types%03d.info.%s", nfile++, date);
+		join(path, sizeof(path), dir, name);
+	} while (0 == access(path, F_OK));
+	sqt_host_normalise_types(r, d);
+	FILE *fp = fopen(path, "w");
+	if (!fp) return -1;
+	const size_t ST = (size_t)S * T;
+	fprintf(fp, "# per-type partials: n_types %d, atoms", nt);
+	for (int a = 0; a < nt; a++) fprintf(fp, " %lld", r->nPtls_a[a]);
+	fprintf(fp, ", kVal %7.3f deltaT %7.3f rVal %7.3f\n", r->kVal, (d->nCSkip + 1) * d->deltaT, d->rVal);
+	if (flag_f)
+		for (int a = 0; a < nt; a++)
+			for (int b = 0; b < nt; b++) {
+				fprintf(fp, "# F_ab %d %d\n", a + 1, b + 1);
+				const double *t = r->avF_ab + ((size_t)a * nt + b) * ST;
+				for (int lag = 0; lag < T; lag++) {
+					fprintf(fp, "%7.3f", lag * 1. * d->deltaT);
+					for (int nk = 0; nk < S; nk++) fprintf(fp, " %8.4e", t[(size_t)nk * T + lag]);
+					fprintf(fp, "\n");
+				}
+				fprintf(fp, "\n");
+			}
+	if (flag_F)
+		for (int a = 0; a < nt; a++) {
+			fprintf(fp, "# F_s_a %d\n", a + 1);
+			const double *t = r->avF_s_a + (size_t)a * ST;
+			for (int lag = 0; lag < T; lag++) {
+				fprintf(fp, "%7.3f", lag * 1. * d->deltaT);
+				for (int nk = 0; nk < S; nk++) fprintf(fp, " %8.4e", t[(size_t)nk * T + lag]);
+				fprintf(fp, "\n");
+			}
+			fprintf(fp, "\n");
+		}
+	if (flag_f && flag_t)
+		for (int a = 0; a < nt; a++) {
+			fprintf(fp, "# self-vanHove_a %d\n", a + 1);
+			const double *t = r->avDrTable_a + (size_t)a * ST;
+			for (int lag = 0; lag < T; lag++) {
+				for (int nr = 0; nr < S; nr++) fprintf(fp, " %8.4e", t[(size_t)nr * T + lag]);
+				fprintf(fp, "\n");
+			}
+			fprintf(fp, "\n");
+		}
+	if (flag_t) {
+		fprintf(fp, "# time, then MSD_a MQD_a per species\n");
+		for (int lag = 0; lag < T; lag++) {
+			fprintf(fp, "%8.4f", lag * d->deltaT * (d->nCSkip + 1));
+			for (int a = 0; a < nt; a++) fprintf(fp, " %8.4g %8.4g", r->rrMSD_a[a * T + lag], r->rrMQD_a[a * T + lag]);
+			fprintf(fp, "\n");
+		}
+	}
+	fclose(fp);
 	return 0;
 }
 

@@ -79,6 +79,18 @@ struct sqt_handle {
 	// -M, -s
 	double *d_kmu0, *d_sumVR_state, *d_orgSumVR, *d_bufMSR1, *d_bufMSR2, *d_axis_partial, *d_vr_partial;
 	long long vr_frames;      // processed frames so far (parity of the double-buffered sum_n v (x) r state)
+	// per-type partials: the frame is regrouped by species on the device (each species a contiguous
+	// range starting at a multiple of 32 particles), every per-particle pass runs once per range
+	int n_types;              // 0 / 1: off
+	std::vector<int> h_types; // species (1 .. n_types) of this shard's atoms, dump order (sqt_set_types)
+	int type_start[SQT_MAX_TYPES], type_count[SQT_MAX_TYPES];
+	long long type_total[SQT_MAX_TYPES]; // atoms of each species over all shards
+	int n_sorted;             // length of the grouped frame (sum of the ranges, each padded to 32)
+	int *d_perm;              // [n_sorted]: dump-order index of the particle at a grouped position, -1 in the padding
+	double *d_raw[2];         // host frames land here in dump order before they are regrouped into d_cur
+	double *d_bufFs_t, *d_bufMSD_t, *d_bufMQD_t, *d_rho0_t, *d_bufFab;
+	int *d_bufHist_t;
+	size_t tav_off;           // offset of the species' running sums inside d_avblk
 	cudaStream_t s_main, s_copy, s_coll, s_aux;
 	cudaEvent_t ev_red, ev_coll, ev_rho, ev_rhoc, ev_prod, ev_t0, ev_t1;
 	bool coll_pending, rhoc_pending;
@@ -123,9 +135,23 @@ extern "C" int sqt_results_alloc(sqt_results *r, int S, int T)
 	return SQT_OK;
 }
 
+extern "C" int sqt_results_alloc_types(sqt_results *r, int n_types)
+{
+	if (!r || n_types < 2 || n_types > SQT_MAX_TYPES || r->nCSpatial < 1) return SQT_ERR_ARG;
+	const size_t ST = (size_t)r->nCSpatial * r->nCTime, T = r->nCTime, nt = n_types;
+	if (!(r->avF_ab = (double *)calloc(nt * nt * ST, sizeof(double)))) return SQT_ERR_NOMEM;
+	if (!(r->avF_s_a = (double *)calloc(nt * ST, sizeof(double)))) return SQT_ERR_NOMEM;
+	if (!(r->avDrTable_a = (double *)calloc(nt * ST, sizeof(double)))) return SQT_ERR_NOMEM;
+	if (!(r->rrMSD_a = (double *)calloc(nt * T, sizeof(double)))) return SQT_ERR_NOMEM;
+	if (!(r->rrMQD_a = (double *)calloc(nt * T, sizeof(double)))) return SQT_ERR_NOMEM;
+	r->n_types = n_types;
+	return SQT_OK;
+}
+
 extern "C" void sqt_results_free(sqt_results *r)
 {
 	if (!r) return;
+	free(r->avF_ab); free(r->avF_s_a); free(r->avDrTable_a); free(r->rrMSD_a); free(r->rrMQD_a);
 	free(r->avF_qq2); free(r->StdDevF_qq2); free(r->avF_s_qq2); free(r->StdDevF_s_qq2);
 	free(r->avF_d_qq2); free(r->StdDevF_d_qq2); free(r->avDrTable);
 	free(r->rrMSDAv); free(r->rrMQDAv); free(r->rrMSDCMAv);
@@ -163,6 +189,11 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	if ((p->flag_V || p->flag_M) && p->nCSpatial > SQT_MAX_NCSPATIAL_V)
 		return fail(h, SQT_ERR_ARG, "sqt_create: -V / -M need nCSpatial <= %d (got %d)", SQT_MAX_NCSPATIAL_V, p->nCSpatial);
 	if (!(p->rVal > 0)) return fail(h, SQT_ERR_ARG, "sqt_create: rVal must be > 0");
+	if (p->n_types < 0 || p->n_types > SQT_MAX_TYPES) return fail(h, SQT_ERR_ARG, "sqt_create: n_types must be 0 .. %d", SQT_MAX_TYPES);
+	if (p->n_types > 1 && (p->flag_V || p->flag_M || p->flag_s))
+		return fail(h, SQT_ERR_ARG, "sqt_create: per-type partials (n_types > 1) do not combine with -V / -M / -s");
+	if (p->n_types > 1 && p->nCSpatial > SQT_MAX_NCSPATIAL_V)
+		return fail(h, SQT_ERR_ARG, "sqt_create: per-type partials need nCSpatial <= %d (got %d)", SQT_MAX_NCSPATIAL_V, p->nCSpatial);
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev < 1)
@@ -204,6 +235,10 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->vel_nchunk = h->vel_chunk = 0;
 	h->d_kmu0 = h->d_sumVR_state = h->d_orgSumVR = h->d_bufMSR1 = h->d_bufMSR2 = h->d_axis_partial = h->d_vr_partial = nullptr;
 	h->vr_frames = 0;
+	h->n_types = p->n_types > 1 ? p->n_types : 0;
+	h->n_sorted = 0; h->d_perm = nullptr; h->d_raw[0] = h->d_raw[1] = nullptr; h->tav_off = 0;
+	h->d_bufFs_t = h->d_bufMSD_t = h->d_bufMQD_t = h->d_rho0_t = h->d_bufFab = nullptr; h->d_bufHist_t = nullptr;
+	for (int t = 0; t < SQT_MAX_TYPES; ++t) { h->type_start[t] = h->type_count[t] = 0; h->type_total[t] = 0; }
 	h->latched = false; h->latched_count = 0; h->latched_limit = 0;
 	h->comm = nullptr; h->rank = 0; h->nranks = 1; h->launches = 0; h->prof = false; h->prof_used = 0;
 	h->coll_pending = h->rhoc_pending = false;
@@ -258,14 +293,23 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	h->rho_n = 6 * (int)S + 3;
 	h->blk_v = h->flag_V ? 1 : -1;
 	h->blk_m = h->flag_M ? (h->flag_V ? 2 : 1) : -1;
-	h->n_fields = 1 + (h->flag_V ? 1 : 0) + (h->flag_M ? 1 : 0);
+	h->n_fields = 1 + (h->flag_V ? 1 : 0) + (h->flag_M ? 1 : 0) + h->n_types; // (per-type partials: rho_a(k) in blocks 1 .. n_types)
 	h->off_vr = h->n_fields * h->rho_n;
 	h->coll_n = h->off_vr + (h->flag_s ? 9 : 0);
 	h->off_scratch = h->off_vr + 16;
 	CUC(cudaMalloc(&h->d_rho_cur, sizeof(double) * (h->off_scratch + h->rho_n))); // rho + sum r | kvel + sum v (-V) | kmu + sum mu (-M) | sum v (x) r (-s) | scratch
 	CUC(cudaMemset(h->d_rho_cur, 0, sizeof(double) * (h->off_scratch + h->rho_n)));
-	CUC(cudaMalloc(&h->d_cblk, sizeof(double) * (2 * T * S + 6 * T)));
-	CUC(cudaMemset(h->d_cblk, 0, sizeof(double) * (2 * T * S + 6 * T)));
+	const size_t cblk_n = 2 * T * S + 6 * T + (size_t)h->n_types * (2 * T * S + 2 * T);
+	CUC(cudaMalloc(&h->d_cblk, sizeof(double) * cblk_n));
+	CUC(cudaMemset(h->d_cblk, 0, sizeof(double) * cblk_n));
+	if (h->n_types) {
+		const size_t nt = h->n_types;
+		double **tb[] = { &h->d_bufFs_t, &h->d_bufMSD_t, &h->d_bufMQD_t, &h->d_rho0_t, &h->d_bufFab };
+		const size_t tn[] = { nt * B * T * S, nt * B * T, nt * B * T, B * nt * 6 * S, nt * nt * B * T * S };
+		for (int i = 0; i < 5; ++i) { CUC(cudaMalloc(tb[i], sizeof(double) * tn[i])); CUC(cudaMemset(*tb[i], 0, sizeof(double) * tn[i])); }
+		CUC(cudaMalloc(&h->d_bufHist_t, sizeof(int) * nt * B * T * S));
+		CUC(cudaMemset(h->d_bufHist_t, 0, sizeof(int) * nt * B * T * S));
+	}
 	if (h->flag_M) {
 		CUC(cudaMalloc(&h->d_kmu0, sizeof(double) * B * 6 * S));
 		CUC(cudaMemset(h->d_kmu0, 0, sizeof(double) * B * 6 * S));
@@ -293,6 +337,8 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 		CUC(cudaMemset(h->d_sumv0, 0, sizeof(double) * B * 3));
 	}
 	h->avblk_n = SQT_N2D * S * T + SQT_N1D * T;
+	h->tav_off = h->avblk_n;
+	if (h->n_types) h->avblk_n += (size_t)h->n_types * h->n_types * S * T + 2 * (size_t)h->n_types * S * T + 2 * (size_t)h->n_types * T;
 	CUC(cudaMalloc(&h->d_avblk, sizeof(double) * h->avblk_n));
 	CUC(cudaMemset(h->d_avblk, 0, sizeof(double) * h->avblk_n)); // ZeroAvSpacetimeCorr, lmp2sqt.c:1921
 	CUC(cudaMalloc(&h->d_latblk, sizeof(double) * h->avblk_n));
@@ -314,8 +360,8 @@ static void release_sized(sqt_handle *h)
 	for (int i = 0; i < 2; ++i) { cudaFree(h->d_cur[i]); h->d_cur[i] = nullptr; }
 	cudaFree(h->d_ring); cudaFree(h->d_partial); cudaFree(h->d_tile_ctr); cudaFree(h->d_mma_partial); cudaFree(h->d_mma_ctr);
 	cudaFree(h->d_rho_partial); cudaFree(h->d_mma_extra); cudaFree(h->d_rho_extra); cudaFree(h->d_vring); cudaFree(h->d_vpartial);
-	cudaFree(h->d_axis_partial); cudaFree(h->d_vr_partial);
-	h->d_axis_partial = h->d_vr_partial = nullptr;
+	cudaFree(h->d_axis_partial); cudaFree(h->d_vr_partial); cudaFree(h->d_perm); cudaFree(h->d_raw[0]); cudaFree(h->d_raw[1]);
+	h->d_axis_partial = h->d_vr_partial = nullptr; h->d_perm = nullptr; h->d_raw[0] = h->d_raw[1] = nullptr;
 	h->d_ring = h->d_partial = h->d_mma_partial = h->d_rho_partial = h->d_mma_extra = h->d_rho_extra = h->d_vring = h->d_vpartial = nullptr;
 	h->d_tile_ctr = h->d_mma_ctr = nullptr;
 	h->sized = false;
@@ -338,6 +384,7 @@ extern "C" void sqt_destroy(sqt_handle *h)
 	cudaFree(h->d_rho0); cudaFree(h->d_sumr0); cudaFree(h->d_invL0); cudaFree(h->d_rho_cur); cudaFree(h->d_cblk);
 	cudaFree(h->d_thr); cudaFree(h->d_avblk); cudaFree(h->d_latblk);
 	cudaFree(h->d_bufC2); cudaFree(h->d_bufCvv); cudaFree(h->d_bufCvcm); cudaFree(h->d_kvel0); cudaFree(h->d_sumv0);
+	cudaFree(h->d_bufFs_t); cudaFree(h->d_bufMSD_t); cudaFree(h->d_bufMQD_t); cudaFree(h->d_rho0_t); cudaFree(h->d_bufFab); cudaFree(h->d_bufHist_t);
 	cudaFree(h->d_kmu0); cudaFree(h->d_sumVR_state); cudaFree(h->d_orgSumVR); cudaFree(h->d_bufMSR1); cudaFree(h->d_bufMSR2);
 	for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
 	cudaEvent_t evs[] = { h->ev_red, h->ev_coll, h->ev_rho, h->ev_rhoc, h->ev_prod, h->ev_t0, h->ev_t1 };
@@ -400,6 +447,33 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 	h->n_local = n_local;
 	h->nPtls = n_total;
 	h->cur_pitch = ((long long)n_local + 31) & ~31LL;
+	if (h->n_types) { // group the shard by species: ranges padded to 32 particles, stable inside a species
+		if ((int)h->h_types.size() != n_local)
+			return fail(h, SQT_ERR_STATE, "per-type partials: sqt_set_types must give the species of the shard's %d atoms before the first frame (got %zu)",
+			            n_local, h->h_types.size());
+		for (int t = 0; t < h->n_types; ++t) h->type_count[t] = 0;
+		for (int i = 0; i < n_local; ++i) h->type_count[h->h_types[i] - 1]++;
+		int pos = 0;
+		for (int t = 0; t < h->n_types; ++t) { h->type_start[t] = pos; pos += (h->type_count[t] + 31) & ~31; }
+		h->n_sorted = pos > 0 ? pos : 32;
+		std::vector<int> perm(h->n_sorted, -1), fill(h->n_types, 0);
+		for (int i = 0; i < n_local; ++i) { const int t = h->h_types[i] - 1; perm[h->type_start[t] + fill[t]++] = i; }
+		CU(cudaMalloc(&h->d_perm, sizeof(int) * h->n_sorted));
+		CU(cudaMemcpy(h->d_perm, perm.data(), sizeof(int) * h->n_sorted, cudaMemcpyHostToDevice));
+		for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_raw[i], sizeof(double) * h->ncomp * (size_t)n_local));
+		h->cur_pitch = h->n_sorted;
+		// atoms of each species over all shards (normalisation of F_s,a and MSD_a)
+		double cnt[SQT_MAX_TYPES];
+		for (int t = 0; t < h->n_types; ++t) cnt[t] = (double)h->type_count[t];
+		if (h->comm) {
+			CU(cudaMemcpy(h->d_cblk, cnt, sizeof(double) * h->n_types, cudaMemcpyHostToDevice));
+			if (sqt_comm_allreduce_f64(h->comm, h->d_cblk, (size_t)h->n_types, h->s_coll, h->err, sizeof(h->err))) return SQT_ERR_NCCL;
+			CU(cudaStreamSynchronize(h->s_coll));
+			CU(cudaMemcpy(cnt, h->d_cblk, sizeof(double) * h->n_types, cudaMemcpyDeviceToHost));
+			CU(cudaMemset(h->d_cblk, 0, sizeof(double) * h->n_types));
+		}
+		for (int t = 0; t < h->n_types; ++t) h->type_total[t] = (long long)(cnt[t] + 0.5);
+	}
 	for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_cur[i], sizeof(double) * h->ncomp * h->cur_pitch));
 	// Which kernel serves the per-particle terms.  F_s needs the nCSpatial Chebyshev chains (-F); MSD, MQD and the van Hove
 	// table (-t) only the displacement: without -F the particle-per-lane kernel runs with a single chain, and with neither
@@ -411,7 +485,7 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 	h->vc.on = 0;
 	if (want_self && !h->mc.on && h->mc.geo) { // (rho(k) comes from the tensor-core rho kernel on this path)
 		// without a communicator (and without -V) the whole frame is two launches: rho(k) rides in the vector kernel
-		const int fuse = !h->comm && !h->flag_V && !h->flag_M && !h->flag_s && h->flag_F;
+		const int fuse = !h->comm && !h->flag_V && !h->flag_M && !h->flag_s && !h->n_types && h->flag_F;
 		rc = sqt_pick_vec(h->S, h->flag_F ? h->S : 1, h->B, n_local, h->n_sm, fuse, &h->vc);
 		if (rc != 0) return fail(h, SQT_ERR_CUDA, "vector kernel selection failed (rc=%d)", rc);
 	}
@@ -424,10 +498,10 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 	h->RP = (h->B + 15) & ~15; // 128-byte rows: a warp's 32 origins of one particle/axis are contiguous
 	// the tensor-core kernel walks particles along the warp, so its ring is [slot][axis][particle] (pitch: a multiple of 32
 	// particles); the classic kernel walks slots along the warp: [particle][axis][slot]
-	h->ring_np = ((long long)n_local + 31) & ~31LL;
+	h->ring_np = h->n_types ? h->n_sorted : (((long long)n_local + 31) & ~31LL);
 	size_t ring_bytes = 0;
 	if (h->self_kind != SELF_NONE) {
-		ring_bytes = lane_family ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)n_local;
+		ring_bytes = lane_family ? sizeof(double) * 3 * (size_t)h->B * (size_t)h->ring_np : sizeof(double) * 3 * (size_t)h->RP * (size_t)h->ring_np;
 		cudaError_t e = cudaMalloc(&h->d_ring, ring_bytes);
 		if (e != cudaSuccess) return fail(h, SQT_ERR_NOMEM, "origin ring of %.2f GB does not fit on the device: %s", ring_bytes / 1e9, cudaGetErrorString(e));
 		CU(cudaMemsetAsync(h->d_ring, 0, ring_bytes, h->s_main));
@@ -451,7 +525,7 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		CU(cudaMemsetAsync(h->d_mma_extra, 0, xb, h->s_main));
 	}
 	h->rmc.on = 0;
-	if ((h->self_kind != SELF_CLASSIC || h->flag_V || h->flag_M) && !h->fused) {
+	if ((h->self_kind != SELF_CLASSIC || h->flag_V || h->flag_M || h->n_types) && !h->fused) {
 		const char *rm = getenv("SQT_RHO_MMA");
 		if (!(rm && *rm == '0')) {
 			rc = sqt_pick_rho_mma(h->mc, n_local, h->n_sm, &h->rmc);
@@ -464,8 +538,8 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 			mma_bytes += rb;
 		}
 	}
-	if ((h->flag_V || h->flag_M) && !h->rmc.on)
-		return fail(h, SQT_ERR_ARG, "-V / -M need the tensor-core rho(k) kernel (nCSpatial <= %d, SQT_MMA / SQT_RHO_MMA not 0)", SQT_MAX_NCSPATIAL_V);
+	if ((h->flag_V || h->flag_M || h->n_types) && !h->rmc.on)
+		return fail(h, SQT_ERR_ARG, "-V / -M / per-type partials need the tensor-core rho(k) kernel (nCSpatial <= %d, SQT_MMA / SQT_RHO_MMA not 0)", SQT_MAX_NCSPATIAL_V);
 	if (h->flag_s) {
 		int chunk = 8192, nch = (n_local + chunk - 1) / chunk;
 		if (nch > 2048) { nch = 2048; chunk = (n_local + nch - 1) / nch; nch = (n_local + chunk - 1) / chunk; }
@@ -517,8 +591,10 @@ static int size_for_atoms_impl(sqt_handle *h, int n_local, long long n_total)
 		                : h->flag_V ? " (+ velocity-weighted pass, vel_ring_kernel)" : h->flag_M ? " (+ dipole-weighted pass)" : "");
 	if (h->self_kind != SELF_CLASSIC)
 		off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "%s%s", h->rmc.on ? "; unused: " : "", classic);
-	snprintf(h->cfg + off, sizeof(h->cfg) - off, "; slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB", h->B, SQT_NVIRT, ring_bytes / 1e9,
-	         (part_bytes + mma_bytes) / 1e6);
+	off += snprintf(h->cfg + off, sizeof(h->cfg) - off, "; slots=%d(+%d virtual) ring=%.3fGB partials=%.1fMB", h->B, SQT_NVIRT, ring_bytes / 1e9,
+	                (part_bytes + mma_bytes) / 1e6);
+	if (h->n_types && off < (int)sizeof(h->cfg))
+		snprintf(h->cfg + off, sizeof(h->cfg) - off, "; per-type partials: %d species, frame regrouped on the device, one pass per species", h->n_types);
 	h->sized = true;
 	return SQT_OK;
 }
@@ -564,6 +640,8 @@ static int stage_collective(sqt_handle *h, int p, long long n_total, bool split)
 	ca.flag_s = h->flag_s; ca.off_vr = h->off_vr; ca.vr_cumulative = !h->flag_f; ca.vr_parity = (int)(h->vr_frames & 1);
 	ca.sumVR_state = h->d_sumVR_state; ca.orgSumVR = h->d_orgSumVR; ca.bufMSR2 = h->d_bufMSR2;
 	h->vr_frames++;
+	ca.n_types = h->n_types; ca.rho0_t = h->d_rho0_t; ca.bufFab = h->d_bufFab;
+	if (!h->flag_V && !h->flag_M) ca.rho_n = h->rho_n;
 	int rc = sqt_launch_collective(ca, h->s_coll);
 	if (rc) return fail(h, SQT_ERR_CUDA, "collective_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 	h->launches++;
@@ -588,11 +666,14 @@ static int accumulate_completed(sqt_handle *h, int done_on_device, int *status)
 			aa.bufHist = h->d_bufHist; aa.cblk = h->d_cblk;
 			aa.flag_f = h->flag_f; aa.flag_F = h->flag_F; aa.flag_t = h->flag_t; aa.flag_V = h->flag_V; aa.flag_M = h->flag_M; aa.flag_s = h->flag_s;
 			aa.bufC2 = h->d_bufC2; aa.bufCvv = h->d_bufCvv; aa.bufCvcm = h->d_bufCvcm; aa.bufMSR1 = h->d_bufMSR1; aa.bufMSR2 = h->d_bufMSR2;
+			aa.n_types = h->n_types; aa.bufFs_t = h->d_bufFs_t; aa.bufMSD_t = h->d_bufMSD_t; aa.bufMQD_t = h->d_bufMQD_t; aa.bufHist_t = h->d_bufHist_t;
+			aa.bufFab = h->d_bufFab; aa.tav = h->d_avblk + h->tav_off;
 			for (int i = 0; i < SQT_N2D; ++i) aa.av[i] = h->d_avblk + (size_t)i * ST;
 			for (int i = 0; i < SQT_N1D; ++i) aa.av1[i] = h->d_avblk + SQT_N2D * ST + (size_t)i * T;
 			rc = sqt_launch_pack(aa, h->s_coll);
 			if (rc) return fail(h, SQT_ERR_CUDA, "buffer_pack_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-			if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, 2 * ST + (h->flag_s ? 6 : 3) * (size_t)T, h->s_coll, h->err, sizeof(h->err)))
+			const size_t cb_n = h->n_types ? 2 * ST + 6 * (size_t)T + (size_t)h->n_types * (2 * ST + 2 * (size_t)T) : 2 * ST + (h->flag_s ? 6 : 3) * (size_t)T;
+			if (h->comm && sqt_comm_allreduce_f64(h->comm, h->d_cblk, cb_n, h->s_coll, h->err, sizeof(h->err)))
 				return SQT_ERR_NCCL;
 			rc = sqt_launch_accumulate(aa, h->s_coll);
 			if (rc) return fail(h, SQT_ERR_CUDA, "buffer_accumulate_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -647,6 +728,13 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 	int varbox = 0;
 	for (int nb = 0; nb < B; ++nb)
 		if (h->count[nb] > 0 && h->h_invL0[nb] != invL) { varbox = 1; break; }
+
+	if (h->n_types) { // per-type partials: regroup the frame by species (24 B per atom read and written: HBM bound, negligible)
+		rc = sqt_launch_gather(h->d_cur[slot], h->cur_pitch, cur, cur_pitch, h->d_perm, h->n_sorted, h->ncomp, h->s_main);
+		if (rc) return fail(h, SQT_ERR_CUDA, "gather_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+		h->launches++;
+		cur = h->d_cur[slot]; cur_pitch = h->cur_pitch;
+	}
 
 	if (h->fused) {
 		// ---- small shapes, no communicator: two launches per frame -----------------------------------------------------------
@@ -705,9 +793,25 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 		qa.cur = cur; qa.wt = nullptr; qa.kfac = 0.0; qa.partial = h->d_rho_partial; qa.extra = h->d_rho_extra; qa.spout = h->mc.SPOUT;
 		qa.rho_cur = h->d_rho_cur; qa.cur_pitch = cur_pitch;
 		qa.n_local = h->n_local; qa.total_warps = h->rmc.total_warps; qa.n_sets = h->rmc.blocks; qa.nCS = S; qa.S = h->mc.S; qa.NT = h->mc.NT; qa.invL = invL;
-		rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches += 2;
+		if (h->n_types) { // rho_a(k) of every species from its own range, then rho(k) as their sum
+			for (int t = 0; t < h->n_types; ++t) {
+				double *blk = h->d_rho_cur + (size_t)(1 + t) * h->rho_n;
+				if (h->type_count[t] == 0) { CU(cudaMemsetAsync(blk, 0, sizeof(double) * h->rho_n, h->s_main)); continue; }
+				qa.cur = cur + h->type_start[t]; qa.n_local = h->type_count[t]; qa.rho_cur = blk;
+				rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
+				if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+				h->launches += 2;
+			}
+			TypeSumArgs ts;
+			ts.rho_cur = h->d_rho_cur; ts.rho_n = h->rho_n; ts.n_types = h->n_types;
+			rc = sqt_launch_type_sum(ts, h->s_main);
+			if (rc) return fail(h, SQT_ERR_CUDA, "type_sum_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+			h->launches++;
+		} else {
+			rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
+			if (rc) return fail(h, SQT_ERR_CUDA, "rho_mma_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+			h->launches += 2;
+		}
 		if (h->flag_V) { // kvel_q1 (lmp2sqt.c:1203-1208): the same pass with the velocity component as the particle's weight
 			qa.wt = cur + h->comp_v * cur_pitch; qa.kfac = h->kVal; qa.rho_cur = h->d_rho_cur + (size_t)h->blk_v * h->rho_n;
 			rc = sqt_launch_rho_mma(h->mc, h->rmc, qa, h->s_main);
@@ -729,88 +833,112 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 	}
 
 	// ---- stage B: the per-particle terms over the origin ring ---------------------------------------------------------
-	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-	if (h->prof) { pe0 = prof_event(h); pe1 = prof_event(h); CU(cudaEventRecord(pe0, h->s_main)); }
-	MmaArgs ma;
-	if (h->self_kind == SELF_MMA || h->self_kind == SELF_VEC) {
-		const bool mm = h->self_kind == SELF_MMA;
-		ma.cur = cur; ma.ring = h->d_ring; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
-		ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = cur_pitch; ma.n_local = h->n_local;
-		ma.tile = mm ? h->mc.tile : h->vc.tile; ma.ntiles = mm ? h->mc.ntiles : h->vc.ntiles; ma.NWSG = mm ? h->mc.NWSG : h->vc.NWSG; ma.NWSG_real = ma.NWSG;
-		ma.KW = mm ? h->mc.KW : h->vc.KW; ma.total_warps = mm ? h->mc.total_warps : h->vc.total_warps; ma.dynamic = mm ? h->mc.dynamic : h->vc.dynamic;
-		ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = mm ? h->mc.S : 0; ma.NT = mm ? h->mc.NT : 0; ma.invL = invL;
-		ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
-		ma.done_ctr = nullptr; ma.bufFs = ma.bufMSD = ma.bufMQD = ma.rho_cur = nullptr;
-		rc = mm ? sqt_launch_mma(h->mc, ma, h->s_main) : sqt_launch_vec(h->vc, ma, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "self_ring_mma_kernel" : "self_ring_vec_kernel", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-	}
+	// One pass over the whole shard, or (per-type partials) one pass per species over its contiguous range of the grouped
+	// frame: same kernels, the range's offset added to the frame and ring pointers, the species' own result buffers.
+	const bool lane_family = h->self_kind == SELF_MMA || h->self_kind == SELF_VEC;
 	const bool classic_launch = h->self_kind == SELF_CLASSIC || !h->rmc.on; // its own slots, or just the six virtual rho(k) slots
 	const int Bc = h->self_kind == SELF_CLASSIC ? B : 0; // slots the classic kernel treats as real
-	if (classic_launch) {
-		RingArgs ra;
-		ra.cur = cur; ra.ring = h->d_ring; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
-		ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = cur_pitch; ra.n_local = h->n_local;
-		ra.tile = h->kc.tile; ra.ntiles = h->kc.ntiles; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
-		ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = Bc; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
-		ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
-		ra.varbox = varbox;
-		rc = sqt_launch_ring(h->kc, ra, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "self_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-	}
-	if (h->prof) CU(cudaEventRecord(pe1, h->s_main));
-
-	// what follows rewrites per-buffer arrays the previous frame's accumulate stage (other stream) may still read
-	if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
-	if (h->d_vring) { // -V -t: rrCvv over the origin-velocity ring (lmp2sqt.c:1397-1401, 1441)
-		VelArgs va;
-		va.vcur = cur + h->comp_v * cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
-		va.cur_pitch = cur_pitch; va.RP = h->ring_np; va.n_local = h->n_local; va.nchunk = h->vel_nchunk; va.chunk = h->vel_chunk;
-		va.p = p; va.T = T; va.B = B;
-		rc = sqt_launch_vel(va, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "vel_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches += 2;
-	}
-	if (h->flag_s) { // -s: rrMSR1_R, the per-axis squares of the displacements (lmp2sqt.c:1434-1436): one more pass over the origin ring
-		const bool lane = h->self_kind == SELF_MMA || h->self_kind == SELF_VEC;
-		AxisMsdArgs xa;
-		xa.cur = cur; xa.ring = h->d_ring; xa.partial = h->d_axis_partial; xa.bufMSR1 = h->d_bufMSR1; xa.cur_pitch = cur_pitch;
-		xa.s_slot = lane ? 3 * h->ring_np : 1; xa.s_axis = lane ? h->ring_np : h->RP; xa.s_ptl = lane ? 1 : 3 * (long long)h->RP;
-		xa.n_local = h->n_local; xa.nchunk = h->vel_nchunk; xa.chunk = h->vel_chunk; xa.p = p; xa.T = T; xa.B = B;
-		rc = sqt_launch_axis_msd(xa, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "axis_msd_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches += 2;
-	}
-	CU(cudaEventRecord(h->ev_ring[slot], h->s_main)); // d_cur[slot] may be overwritten by the copy of the frame after next
-
-	if (h->self_kind == SELF_MMA || h->self_kind == SELF_VEC) {
-		const bool mm = h->self_kind == SELF_MMA;
-		MmaReduceArgs mr;
-		mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = mm ? h->mc.SPOUT : 0; mr.n_local = h->n_local;
-		mr.KW = mm ? h->mc.KW : h->vc.KW; mr.NWSG = mm ? h->mc.NWSG : h->vc.NWSG;
-		mr.S = mm ? h->mc.S : 0; mr.NT = mm ? h->mc.NT : h->vc.C + 2; mr.SPW = mm ? h->mc.SPW : h->vc.SPW;
-		mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = h->d_bufHist;
-		mr.bufFs = h->d_bufFs; mr.bufMSD = h->d_bufMSD; mr.bufMQD = h->d_bufMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
-		rc = mm ? sqt_launch_mma_reduce(mr, h->s_main) : sqt_launch_vec_reduce(mr, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "mma_reduce_kernel" : "vec_reduce_kernel", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-	}
-	if (classic_launch) {
-		ReduceArgs rr;
-		rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
-		rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = h->d_bufHist; rr.bufFs = h->d_bufFs;
-		rr.bufMSD = h->d_bufMSD; rr.bufMQD = h->d_bufMQD; rr.invL0 = h->d_invL0; rr.invL = invL;
-		// with the tensor-core rho kernel on (-V on the recurrence path) rho(k) is already final: the virtual slots' copy goes to scratch
-		rr.rho_cur = h->rmc.on ? h->d_rho_cur + h->off_scratch : h->d_rho_cur;
-		rc = sqt_launch_reduce(rr, h->s_main);
-		if (rc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-		h->launches++;
-		if (!h->rmc.on || h->self_kind == SELF_CLASSIC) {
-			if (h->flag_s) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
-			rc = stage_collective(h, p, n_total, split);
+	auto launch_self = [&](long long off, int cnt) -> int {
+		int lrc;
+		if (lane_family) {
+			const bool mm = h->self_kind == SELF_MMA;
+			const int tile = mm ? h->mc.tile : h->vc.tile;
+			MmaArgs ma;
+			ma.cur = cur + off; ma.ring = h->d_ring + off; ma.partial = h->d_mma_partial; ma.extra = h->d_mma_extra; ma.tile_ctr = h->d_mma_ctr; ma.hist_cur = h->d_hist_cur;
+			ma.invL0 = h->d_invL0; ma.thr = h->d_thr; ma.cur_pitch = cur_pitch; ma.n_local = cnt;
+			ma.tile = tile; ma.ntiles = (cnt + tile - 1) / tile; ma.NWSG = mm ? h->mc.NWSG : h->vc.NWSG; ma.NWSG_real = ma.NWSG;
+			ma.KW = mm ? h->mc.KW : h->vc.KW; ma.total_warps = mm ? h->mc.total_warps : h->vc.total_warps; ma.dynamic = mm ? h->mc.dynamic : h->vc.dynamic;
+			ma.p = p; ma.T = T; ma.B = B; ma.nCS = S; ma.RP = h->ring_np; ma.S = mm ? h->mc.S : 0; ma.NT = mm ? h->mc.NT : 0; ma.invL = invL;
+			ma.inv_rVal = (float)(1.0 / h->p.rVal); ma.varbox = varbox;
+			ma.done_ctr = nullptr; ma.bufFs = ma.bufMSD = ma.bufMQD = ma.rho_cur = nullptr;
+			lrc = mm ? sqt_launch_mma(h->mc, ma, h->s_main) : sqt_launch_vec(h->vc, ma, h->s_main);
+			if (lrc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "self_ring_mma_kernel" : "self_ring_vec_kernel", cudaGetErrorString((cudaError_t)lrc));
+			h->launches++;
+		}
+		if (classic_launch) {
+			RingArgs ra;
+			ra.cur = cur + off; ra.ring = h->d_ring ? h->d_ring + off * 3 * h->RP : nullptr; ra.partial = h->d_partial; ra.hist_cur = h->d_hist_cur;
+			ra.invL0 = h->d_invL0; ra.thr = h->d_thr; ra.cur_pitch = cur_pitch; ra.n_local = cnt;
+			ra.tile = h->kc.tile; ra.ntiles = (cnt + h->kc.tile - 1) / h->kc.tile; ra.NWSG = h->kc.NWSG; ra.KW = h->kc.KW; ra.total_warps = h->kc.total_warps;
+			ra.dynamic = h->kc.dynamic; ra.tile_ctr = h->d_tile_ctr; ra.p = p; ra.T = T; ra.B = Bc; ra.nCS = S; ra.RP = h->RP; ra.V0 = h->kc.V0;
+			ra.SPAD = h->kc.SPAD; ra.NV = h->kc.NV; ra.CT = h->kc.CT; ra.invL = invL; ra.inv_rVal = (float)(1.0 / h->p.rVal);
+			ra.varbox = varbox;
+			lrc = sqt_launch_ring(h->kc, ra, h->s_main);
+			if (lrc) return fail(h, SQT_ERR_CUDA, "self_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+			h->launches++;
+		}
+		return SQT_OK;
+	};
+	auto launch_reduce = [&](int cnt, double *bFs, double *bMSD, double *bMQD, int *bHist) -> int {
+		int lrc;
+		if (lane_family) {
+			const bool mm = h->self_kind == SELF_MMA;
+			MmaReduceArgs mr;
+			mr.partial = h->d_mma_partial; mr.extra = h->d_mma_extra; mr.spout = mm ? h->mc.SPOUT : 0; mr.n_local = cnt;
+			mr.KW = mm ? h->mc.KW : h->vc.KW; mr.NWSG = mm ? h->mc.NWSG : h->vc.NWSG;
+			mr.S = mm ? h->mc.S : 0; mr.NT = mm ? h->mc.NT : h->vc.C + 2; mr.SPW = mm ? h->mc.SPW : h->vc.SPW;
+			mr.p = p; mr.T = T; mr.B = B; mr.nCS = S; mr.tile_ctr = h->d_mma_ctr; mr.hist_cur = h->d_hist_cur; mr.bufHist = bHist;
+			mr.bufFs = bFs; mr.bufMSD = bMSD; mr.bufMQD = bMQD; mr.invL0 = h->d_invL0; mr.invL = invL;
+			lrc = mm ? sqt_launch_mma_reduce(mr, h->s_main) : sqt_launch_vec_reduce(mr, h->s_main);
+			if (lrc) return fail(h, SQT_ERR_CUDA, "%s launch failed: %s", mm ? "mma_reduce_kernel" : "vec_reduce_kernel", cudaGetErrorString((cudaError_t)lrc));
+			h->launches++;
+		}
+		if (classic_launch) {
+			ReduceArgs rr;
+			rr.partial = h->d_partial; rr.KW = h->kc.KW; rr.NWSG = h->kc.NWSG; rr.tile_ctr = h->d_tile_ctr; rr.NV = h->kc.NV; rr.SPAD = h->kc.SPAD; rr.CT = h->kc.CT; rr.V0 = h->kc.V0; rr.G = h->kc.G;
+			rr.p = p; rr.T = T; rr.B = Bc; rr.nCS = S; rr.hist_cur = h->d_hist_cur; rr.bufHist = bHist; rr.bufFs = bFs;
+			rr.bufMSD = bMSD; rr.bufMQD = bMQD; rr.invL0 = h->d_invL0; rr.invL = invL;
+			// with the tensor-core rho kernel on (-V / -M / per-type partials on the recurrence path) rho(k) is already final: the virtual slots' copy goes to scratch
+			rr.rho_cur = h->rmc.on ? h->d_rho_cur + h->off_scratch : h->d_rho_cur;
+			lrc = sqt_launch_reduce(rr, h->s_main);
+			if (lrc) return fail(h, SQT_ERR_CUDA, "frame_reduce_kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+			h->launches++;
+		}
+		return SQT_OK;
+	};
+	const bool typed = h->n_types > 1;
+	const int n_ranges = typed ? h->n_types : 1;
+	const size_t BTS = (size_t)B * T * S, BT = (size_t)B * T;
+	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+	if (h->prof) { pe0 = prof_event(h); pe1 = prof_event(h); CU(cudaEventRecord(pe0, h->s_main)); }
+	for (int ti = 0; ti < n_ranges; ++ti) {
+		const long long off = typed ? h->type_start[ti] : 0;
+		const int cnt = typed ? h->type_count[ti] : h->n_local;
+		if (cnt > 0) { rc = launch_self(off, cnt); if (rc) return rc; }
+		if (ti == n_ranges - 1 && h->prof) CU(cudaEventRecord(pe1, h->s_main)); // (the species' reduce kernels in between are counted in)
+		if (ti == 0) {
+			// what follows rewrites per-buffer arrays the previous frame's accumulate stage (other stream) may still read
+			if (split && h->coll_pending) CU(cudaStreamWaitEvent(h->s_main, h->ev_coll, 0));
+			if (h->d_vring) { // -V -t: rrCvv over the origin-velocity ring (lmp2sqt.c:1397-1401, 1441)
+				VelArgs va;
+				va.vcur = cur + h->comp_v * cur_pitch; va.vring = h->d_vring; va.partial = h->d_vpartial; va.bufCvv = h->d_bufCvv;
+				va.cur_pitch = cur_pitch; va.RP = h->ring_np; va.n_local = h->n_local; va.nchunk = h->vel_nchunk; va.chunk = h->vel_chunk;
+				va.p = p; va.T = T; va.B = B;
+				rc = sqt_launch_vel(va, h->s_main);
+				if (rc) return fail(h, SQT_ERR_CUDA, "vel_ring_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+				h->launches += 2;
+			}
+			if (h->flag_s) { // -s: rrMSR1_R, the per-axis squares of the displacements (lmp2sqt.c:1434-1436): one more pass over the origin ring
+				AxisMsdArgs xa;
+				xa.cur = cur; xa.ring = h->d_ring; xa.partial = h->d_axis_partial; xa.bufMSR1 = h->d_bufMSR1; xa.cur_pitch = cur_pitch;
+				xa.s_slot = lane_family ? 3 * h->ring_np : 1; xa.s_axis = lane_family ? h->ring_np : h->RP; xa.s_ptl = lane_family ? 1 : 3 * (long long)h->RP;
+				xa.n_local = h->n_local; xa.nchunk = h->vel_nchunk; xa.chunk = h->vel_chunk; xa.p = p; xa.T = T; xa.B = B;
+				rc = sqt_launch_axis_msd(xa, h->s_main);
+				if (rc) return fail(h, SQT_ERR_CUDA, "axis_msd_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+				h->launches += 2;
+			}
+		}
+		if (ti == n_ranges - 1) CU(cudaEventRecord(h->ev_ring[slot], h->s_main)); // d_cur[slot] may be overwritten by the copy of the frame after next
+		if (cnt > 0) {
+			rc = typed ? launch_reduce(cnt, h->d_bufFs_t + ti * BTS, h->d_bufMSD_t + ti * BT, h->d_bufMQD_t + ti * BT, h->d_bufHist_t + ti * BTS)
+			           : launch_reduce(cnt, h->d_bufFs, h->d_bufMSD, h->d_bufMQD, h->d_bufHist);
 			if (rc) return rc;
 		}
+	}
+	if (classic_launch && (!h->rmc.on || h->self_kind == SELF_CLASSIC)) {
+		if (h->flag_s) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
+		rc = stage_collective(h, p, n_total, split);
+		if (rc) return rc;
 	}
 	if (split) {
 		CU(cudaEventRecord(h->ev_red, h->s_main));
@@ -887,13 +1015,26 @@ static int push_common(sqt_handle *h, const double *const *comp, bool on_device,
 		}
 		// cur[slot] is free once the kernels that read it two frames ago have run
 		CU(cudaStreamWaitEvent(h->s_copy, h->ev_ring[slot], 0));
+		double *land = h->n_types ? h->d_raw[slot] : h->d_cur[slot]; // (per-type partials: dump order first, run_frame regroups)
+		const long long land_pitch = h->n_types ? n_local : h->cur_pitch;
 		for (int a = 0; a < h->ncomp; ++a)
-			CU(cudaMemcpyAsync(h->d_cur[slot] + a * h->cur_pitch, src[a], sizeof(double) * n_local, cudaMemcpyHostToDevice, h->s_copy));
+			CU(cudaMemcpyAsync(land + a * land_pitch, src[a], sizeof(double) * n_local, cudaMemcpyHostToDevice, h->s_copy));
 		CU(cudaEventRecord(h->ev_copy[slot], h->s_copy));
 		h->copy_pending[slot] = true;
 		CU(cudaStreamWaitEvent(h->s_main, h->ev_copy[slot], 0));
 	}
-	return run_frame(h, slot, h->d_cur[slot], h->cur_pitch, n_total, xlo, xhi);
+	return h->n_types ? run_frame(h, slot, h->d_raw[slot], n_local, n_total, xlo, xhi) : run_frame(h, slot, h->d_cur[slot], h->cur_pitch, n_total, xlo, xhi);
+}
+
+extern "C" int sqt_set_types(sqt_handle *h, const int *types, int n_atoms_local)
+{
+	if (!h || !types || n_atoms_local < 1) return h ? fail(h, SQT_ERR_ARG, "sqt_set_types: bad arguments") : SQT_ERR_ARG;
+	if (!h->n_types) return fail(h, SQT_ERR_STATE, "sqt_set_types: the handle was created without n_types > 1");
+	if (h->sized) return fail(h, SQT_ERR_STATE, "sqt_set_types: the species must be given before the first frame");
+	for (int i = 0; i < n_atoms_local; ++i)
+		if (types[i] < 1 || types[i] > h->n_types) return fail(h, SQT_ERR_ARG, "sqt_set_types: atom %d has type %d outside 1 .. %d", i, types[i], h->n_types);
+	h->h_types.assign(types, types + n_atoms_local);
+	return SQT_OK;
 }
 
 extern "C" int sqt_push_frame(sqt_handle *h, const double *soa, int n_local, long long n_total, double xlo, double xhi)
@@ -965,6 +1106,18 @@ static int copy_results(sqt_handle *h, const double *d_blk, sqt_results *out, in
 			for (int j = 0; j < 3; ++j) out->rrMSR1_R_Av[3 * t + j] = tmp[j * T + t];
 			for (int j = 0; j < 9; ++j) out->rrMSR2_VR_Av[9 * t + j] = tmp[(3 + j) * T + t];
 		}
+	}
+	out->n_types = 0;
+	if (h->n_types && out->avF_ab) { // the species' sums, allocated by sqt_results_alloc_types
+		const size_t nt = h->n_types;
+		const double *tb = d_blk + h->tav_off;
+		CU(cudaMemcpy(out->avF_ab, tb, sizeof(double) * nt * nt * ST, cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(out->avF_s_a, tb + nt * nt * ST, sizeof(double) * nt * ST, cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(out->avDrTable_a, tb + nt * nt * ST + nt * ST, sizeof(double) * nt * ST, cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(out->rrMSD_a, tb + nt * nt * ST + 2 * nt * ST, sizeof(double) * nt * T, cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(out->rrMQD_a, tb + nt * nt * ST + 2 * nt * ST + nt * T, sizeof(double) * nt * T, cudaMemcpyDeviceToHost));
+		for (size_t t = 0; t < nt; ++t) out->nPtls_a[t] = h->type_total[t];
+		out->n_types = h->n_types;
 	}
 	out->countCorrAv = count;
 	out->limitCorrAv = limit;

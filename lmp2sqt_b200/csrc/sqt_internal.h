@@ -11,6 +11,9 @@
 #define SQT_N2D 15
 #define SQT_N1D 18
 #define SQT_NC2 8            // planes of bufC2, in the order of 2-D arrays 7..14
+#define SQT_MAX_TYPES 8      // per-type partials: species a = 1..n_types
+// with n_types > 1 the running sums continue behind the SQT_N1D arrays:
+//   F_ab [n_types^2] x [nCS][T], F_s,a [n_types] x [nCS][T], van Hove_a [n_types] x [nCS][T], MSD_a [n_types] x [T], MQD_a [n_types] x [T]
 #define SQT_MAX_WPB 4        // warps per block of the ring kernel
 
 // Everything the per-frame ring kernel needs.  Passed by value.
@@ -183,7 +186,16 @@ struct CollectiveArgs {
 	double *sumVR_state;      // [2][9]
 	double *orgSumVR;         // [B][9]
 	double *bufMSR2;          // [B][T][9]
+	// per-type partials: rho_a(k) of the frame in blocks 1 .. n_types of rho_cur (block 0 = their sum), origin copies,
+	// F_ab[lag] = sum over axes of rho_a(t) . rho_b*(t0)
+	int n_types;              // 0 / 1: off
+	double *rho0_t;           // [B][n_types][6 nCS]
+	double *bufFab;           // [n_types * n_types][B][T][nCS], plane a * n_types + b
 };
+struct TypeSumArgs { double *rho_cur; int rho_n, n_types; }; // block 0 = sum of blocks 1 .. n_types, fixed order
+int sqt_launch_type_sum(const TypeSumArgs &a, cudaStream_t st);
+// frame in dump order -> grouped by species (each species' range starts at a multiple of 32 particles): dst[c][i] = src[c][perm[i]]
+int sqt_launch_gather(double *dst, long long dst_pitch, const double *src, long long src_pitch, const int *perm, int n_sorted, int ncomp, cudaStream_t st);
 int sqt_launch_collective(const CollectiveArgs &a, cudaStream_t st);
 
 struct AccumArgs {
@@ -200,6 +212,12 @@ struct AccumArgs {
 	const double *bufC2, *bufCvv, *bufCvcm; // -V / -M: [SQT_NC2][B][T][nCS], [B][T], [B][T]
 	const double *bufMSR1, *bufMSR2;        // -s: [B][T][3] (this shard's particles), [B][T][9]
 	int B;
+	// per-type partials: the reduce kernels wrote per-species buffers [n_types][B][T][nCS] / [n_types][B][T] instead of the plain
+	// ones; pack sums them into the plain block and appends one block per species [Fs TS | MSD T | MQD T | hist TS] to cblk
+	int n_types;
+	const double *bufFs_t, *bufMSD_t, *bufMQD_t, *bufFab;
+	const int *bufHist_t;
+	double *tav;              // type sums behind the SQT_N1D arrays (layout above)
 };
 int sqt_launch_pack(const AccumArgs &a, cudaStream_t st);
 int sqt_launch_accumulate(const AccumArgs &a, cudaStream_t st);

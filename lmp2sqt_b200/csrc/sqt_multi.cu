@@ -207,6 +207,18 @@ extern "C" int sqt_multi_set_limit(sqt_multi *m, int limitCorrAv)
 	return SQT_OK;
 }
 
+extern "C" int sqt_multi_set_types(sqt_multi *m, const int *types, int n_atoms)
+{
+	if (!m || !types || n_atoms < 1) return SQT_ERR_ARG;
+	for (int g = 0; g < m->G; ++g) { // the same contiguous chunks the frames are split into
+		int lo, hi;
+		shard(n_atoms, g, m->G, &lo, &hi);
+		const int rc = sqt_set_types(m->h[g], types + lo, hi - lo);
+		if (rc) return mfail(m, rc, "GPU %d: %s", m->p.device + g, sqt_last_error(m->h[g]));
+	}
+	return SQT_OK;
+}
+
 extern "C" int sqt_multi_begin_file(sqt_multi *m)
 {
 	if (!m) return SQT_ERR_ARG;

@@ -91,12 +91,24 @@ class Deck:
 class Results:
     """Owner of an ``sqt_results`` (raw sums as the engine returns them; ``normalise`` = prePrintProcess)."""
 
-    def __init__(self, nCSpatial: int, nCTime: int):
+    def __init__(self, nCSpatial: int, nCTime: int, n_types: int = 0):
         self.c = SqtResults()
         rc = _lib.engine_lib().sqt_results_alloc(C.byref(self.c), nCSpatial, nCTime)
         if rc:
             raise MemoryError("sqt_results_alloc")
         self.S, self.T = nCSpatial, nCTime
+        self.n_types = n_types if n_types > 1 else 0
+        if self.n_types and _lib.engine_lib().sqt_results_alloc_types(C.byref(self.c), n_types):
+            raise MemoryError("sqt_results_alloc_types")
+
+    def type_arrays(self) -> dict:
+        """Per-type partials (raw sums): F_ab [a][b][S][T], F_s_a / DrTable_a [a][S][T], MSD_a / MQD_a [a][T], N_a [a]."""
+        nt, S, T = self.n_types, self.S, self.T
+        if not nt:
+            return {}
+        g = lambda name, shape: np.ctypeslib.as_array(getattr(self.c, name), shape=shape).copy()
+        return {"avF_ab": g("avF_ab", (nt, nt, S, T)), "avF_s_a": g("avF_s_a", (nt, S, T)), "avDrTable_a": g("avDrTable_a", (nt, S, T)),
+                "rrMSD_a": g("rrMSD_a", (nt, T)), "rrMQD_a": g("rrMQD_a", (nt, T)), "nPtls_a": np.array(list(self.c.nPtls_a)[:nt])}
 
     def __del__(self):
         try:
@@ -113,6 +125,7 @@ class Results:
         d = {n: self.array(n).copy() for n in NAMES2D + NAMES1D + list(NAMES_TENSOR)}
         for k in ("countCorrAv", "limitCorrAv", "nPtls", "g_Vol", "kVal", "first_Vol", "first_limitCorrAv", "number_call_print"):
             d[k] = getattr(self.c, k)
+        d.update(self.type_arrays())
         return d
 
     def normalise(self, deck: Deck, flags: str = "Ft") -> None:
@@ -120,6 +133,10 @@ class Results:
         dk = deck.to_c()
         fl = SqtFlags(*_flag_ints(flags))
         _lib.host_lib().sqt_host_normalise_x(C.byref(self.c), C.byref(dk), C.byref(fl))
+
+    def normalise_types(self, deck: Deck) -> None:
+        dk = deck.to_c()
+        _lib.host_lib().sqt_host_normalise_types(C.byref(self.c), C.byref(dk))
 
     def print_process(self, outdir: str, deck: Deck, flags: str = "Ft", date: str | None = None) -> None:
         """PrintProcess (lmp2sqt.c:338-367): normalise in place and write the reference's files into ``outdir``."""
@@ -134,13 +151,14 @@ class Results:
 class SpacetimeCorr:
     """One GPU's share of the space-time correlation state (the reference's MakeSqtClass + globals)."""
 
-    def __init__(self, deck: Deck, flags: str = "Ft", device: int = 0):
+    def __init__(self, deck: Deck, flags: str = "Ft", device: int = 0, n_types: int = 0):
         self.lib = _lib.engine_lib()
         self.deck = deck
         self.flags = flags
+        self.n_types = n_types if n_types > 1 else 0
         ff, fF, ft, fV, fM, fs = _flag_ints(flags)
         p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
-                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, 0, fV, fM, fs)
+                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, 0, fV, fM, fs, n_types)
         self.ncomp = _ncomp(flags)
         h = C.c_void_p()
         rc = self.lib.sqt_create(C.byref(p), C.byref(h))
@@ -177,6 +195,11 @@ class SpacetimeCorr:
 
     begin_file = InitSpacetimeCorr
 
+    def set_types(self, types: np.ndarray):
+        """Per-type partials: the species (1 .. n_types) of this shard's atoms in dump order, before the first frame."""
+        t = np.ascontiguousarray(types, dtype=np.int32)
+        self._check(self.lib.sqt_set_types(self.h, t.ctypes.data, int(t.shape[0])), "sqt_set_types")
+
     def stage(self, n_local: int) -> np.ndarray:
         """Pinned SoA staging for the next frame as a (3, n) float64 view ((6, n) with -V: x y z vx vy vz)."""
         p = self.lib.sqt_stage_acquire(self.h, int(n_local))
@@ -204,13 +227,13 @@ class SpacetimeCorr:
                            "sqt_push_frame_device")
 
     def fetch(self) -> Results:
-        r = Results(self.S, self.T)
+        r = Results(self.S, self.T, self.n_types)
         self._check(self.lib.sqt_fetch_results(self.h, C.byref(r.c)), "sqt_fetch_results")
         return r
 
     def finish(self) -> Results | None:
         """End of run (lmp2sqt.c:327-333): results to print, or None if a mid-run print already happened."""
-        r = Results(self.S, self.T)
+        r = Results(self.S, self.T, self.n_types)
         rc = self._check(self.lib.sqt_finish(self.h, C.byref(r.c)), "sqt_finish")
         return r if rc == 1 else None
 
@@ -282,12 +305,13 @@ class SpacetimeCorr:
 class MultiSpacetimeCorr:
     """G GPUs behind one caller thread (include/sqt.h, sqt_multi_*): one pinned frame, fan-out by particle chunk."""
 
-    def __init__(self, deck: Deck, flags: str = "Ft", n_gpus: int = 2, device: int = 0):
+    def __init__(self, deck: Deck, flags: str = "Ft", n_gpus: int = 2, device: int = 0, n_types: int = 0):
         self.lib = _lib.engine_lib()
         self.deck, self.flags = deck, flags
+        self.n_types = n_types if n_types > 1 else 0
         ff, fF, ft, fV, fM, fs = _flag_ints(flags)
         p = SqtParams(deck.kVal, deck.deltaT, deck.mass, deck.rVal, deck.limitCorrAv, deck.nCBuffer, deck.nCSpatial,
-                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, n_gpus, fV, fM, fs)
+                      deck.nCTime, deck.nCSkip, ff, fF, ft, device, n_gpus, fV, fM, fs, n_types)
         self.ncomp = _ncomp(flags)
         h = C.c_void_p()
         rc = self.lib.sqt_multi_create(C.byref(p), C.byref(h))
@@ -327,13 +351,17 @@ class MultiSpacetimeCorr:
         _fill_stage(st, self.flags, xyz, vel, mu)
         return self._check(self.lib.sqt_multi_push_frame(self.h, st.ctypes.data, n, float(xlo), float(xhi)), "sqt_multi_push_frame")
 
+    def set_types(self, types: np.ndarray):
+        t = np.ascontiguousarray(types, dtype=np.int32)
+        self._check(self.lib.sqt_multi_set_types(self.h, t.ctypes.data, int(t.shape[0])), "sqt_multi_set_types")
+
     def fetch(self) -> Results:
-        r = Results(self.S, self.T)
+        r = Results(self.S, self.T, self.n_types)
         self._check(self.lib.sqt_multi_fetch_results(self.h, C.byref(r.c)), "sqt_multi_fetch_results")
         return r
 
     def finish(self) -> Results | None:
-        r = Results(self.S, self.T)
+        r = Results(self.S, self.T, self.n_types)
         rc = self._check(self.lib.sqt_multi_finish(self.h, C.byref(r.c)), "sqt_multi_finish")
         return r if rc == 1 else None
 
@@ -427,7 +455,7 @@ def shard_bounds(n_total: int, rank: int, nranks: int) -> tuple[int, int]:
 
 
 def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank: int = 0, nranks: int = 1,
-                     unique_id: bytes | None = None, on_flush=None, n_gpus: int = 0):
+                     unique_id: bytes | None = None, on_flush=None, n_gpus: int = 0, n_types: int = 0):
     """Drive the engine over a list of trajectories (= input files) exactly like the reference's main
     (lmp2sqt.c:200-333), including its limitCorrAv bookkeeping.  Returns (printed Results | None, engine).
     ``n_gpus`` > 0 uses the in-process multi-GPU fan-out (sqt_multi_*) instead of one handle."""
@@ -441,12 +469,16 @@ def run_trajectories(trajs, deck: Deck, flags: str = "Ft", device: int = 0, rank
         if ok:
             limit += (n_snap - deck.nCTime) // (deck.nCTime // B)                    # lmp2sqt.c:244
     if n_gpus > 0:
-        eng = MultiSpacetimeCorr(deck, flags, n_gpus, device)
+        eng = MultiSpacetimeCorr(deck, flags, n_gpus, device, n_types)
     else:
-        eng = SpacetimeCorr(deck, flags, device)
+        eng = SpacetimeCorr(deck, flags, device, n_types)
         if nranks > 1:
             eng.comm_init(unique_id, rank, nranks)
     eng.set_limit(limit)
+    if n_types > 1:  # the dump's `type` column; atoms keep their order, so the first used file's species hold for the run
+        t0 = next(t for t, u in zip(trajs, use) if u)
+        lo, hi = (0, t0.n_atoms) if n_gpus > 0 else shard_bounds(t0.n_atoms, rank, nranks)
+        eng.set_types(t0.types[lo:hi])
     printed = None
     with_v, with_m = ("V" in flags or "s" in flags), "M" in flags
     for t, u in zip(trajs, use):

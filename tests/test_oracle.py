@@ -264,3 +264,26 @@ def test_port_magnet_and_stress_reproduce_committed_reference_fixtures(name):
             tab = [ln.split() for ln in open(os.path.join(d, fn)).read().strip().split("\n")]
             for nt, r in enumerate(tab):
                 assert r[1:] == [("%8.4e" % printed[key][nk, nt]).strip() for nk in range(S)], (fn, nt)
+
+
+def test_per_type_statement_is_anchored_to_the_pinned_restatement():
+    """the reference has no per-type code, so the checker of the per-type kernels (oracle/pytypes.py,
+    numpy) is anchored instead: with every atom in one species it gives the pinned restatement's numbers (= the reference's)
+    to rounding, and for any species assignment the partials sum to them."""
+    import pytypes
+    t1 = synth.make_trajectory(n_cells=2, n_frames=40, seed=5, box_jitter=0.004)
+    t2 = synth.make_trajectory(n_cells=2, n_frames=30, seed=6, box_jitter=0.004)
+    S, T, B = 7, 8, 4
+    for skip in (0, 1):
+        _, raw, _ = pyoracle.run_port(None, S, T, B, nCSkip=skip, limitCorrAv=10**8, files=[t1, t2], flags="Ft", finish=False)
+        one = pytypes.run_types([t1, t2], np.ones(32, int), S, T, B, nCSkip=skip)
+        assert one["countCorrAv"] == raw["countCorrAv"] > 0
+        for a, b in (("avF_ab", "avF"), ("avF_s_a", "avF_s"), ("rrMSD_a", "rrMSDAv"), ("rrMQD_a", "rrMQDAv")):
+            np.testing.assert_allclose(one[a].reshape(raw[b].shape), raw[b], rtol=1e-12, atol=1e-12 * np.abs(raw[b]).max(), err_msg=a)
+        assert np.array_equal(one["avDrTable_a"][0], raw["avDrTable"])
+        ty = (np.arange(32) % 3 == 0).astype(int) + 1
+        two = pytypes.run_types([t1, t2], ty, S, T, B, nCSkip=skip)
+        np.testing.assert_allclose(two["avF_ab"].sum(axis=(0, 1)), raw["avF"], rtol=1e-12, atol=1e-12 * np.abs(raw["avF"]).max())
+        np.testing.assert_allclose(two["avF_s_a"].sum(axis=0), raw["avF_s"], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(two["rrMSD_a"].sum(axis=0), raw["rrMSDAv"], rtol=1e-12)
+        assert np.array_equal(two["avDrTable_a"].sum(axis=0), raw["avDrTable"])
