@@ -193,7 +193,7 @@ def parity_check(world, rank, local_rank, dist):
             "countCorrAv": int(got["countCorrAv"]), "ok": ok}
 
 
-def time_workload(wl, K, W, world, rank, local_rank, dist, n_cells_override=0, with_e2e=True, sampler=None):
+def time_workload(wl, K, W, world, rank, local_rank, dist, n_cells_override=0, with_e2e=True, sampler=None, n_types=0):
     """Fill the ring (untimed), then time K steady-state frames resident in HBM (`value`), the same through host buffers
     (`e2e`), and the dominant kernels' own launches (for the roofline).  Returns a dict of raw measurements."""
     import numpy as np
@@ -222,11 +222,14 @@ def time_workload(wl, K, W, world, rank, local_rank, dist, n_cells_override=0, w
     n_local = hi - lo
     Kvec = 3 * S
     deck = Deck(limitCorrAv=10**9, nCBuffer=B, nCSpatial=S, nCTime=T)
-    eng = SpacetimeCorr(deck, "Ft", device=local_rank)
+    eng = SpacetimeCorr(deck, "Ft", device=local_rank, n_types=n_types)
     if world > 1:
         ids = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         eng.comm_init(ids[0], rank, world)
+    if n_types > 1:      # "types {1,2} 80:20 by id"
+        eng.set_types(np.where((np.arange(lo, hi) + 1) % 5 == 0, 2, 1).astype(np.int32))
+        desc += "; per-type partials, %d species 80:20 by id" % n_types
     src = SynthSource(n_cells, lo, n_local, device=local_rank)
     L = src.L
     eng.InitSpacetimeCorr()
@@ -427,6 +430,14 @@ def main():
                               "gpu_launches": mo["launches"], "kernel": mo["cfg"].split(";")[0]}
             except Exception as ex:  # never lose the headline line to a side measurement
                 others[wl] = {"error": str(ex)}
+        try:   # BASELINE config 4 as written: two species, all partials F_ab / F_s,a beside the totals
+            mo = time_workload("c4", 20, 3, 1, 0, local_rank, dist, with_e2e=False, n_types=2)
+            ro = roofline_of(mo, dfma_tf, dfma_mhz, hbm_peak, hbm_src, 1)
+            others["c4_types"] = {"workload": mo["desc"], "ms_per_step": mo["ms_per_step"], "value": mo["value"], "unit": UNIT, "steps": 20,
+                                  "kernel_ms": mo["ring_ms_avg"], "frac": ro["frac"], "bound": ro["bound"], "gpu_launches": mo["launches"],
+                                  "kernel": mo["cfg"].split(";")[0]}
+        except Exception as ex:
+            others["c4_types"] = {"error": str(ex)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
