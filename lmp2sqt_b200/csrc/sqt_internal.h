@@ -99,6 +99,7 @@ int sqt_launch_mma_reduce(const MmaReduceArgs &a, cudaStream_t st);
 struct VecChoice {
 	int on;
 	int C, SPW, WPB, blocks, occ, regs, NWSG, KW, total_warps, tile, ntiles, dynamic; // C = nCSpatial rounded up to 4
+	int minb;                 // launch-bounds variant (resident blocks per SM the registers are bounded for)
 	int fused, NWSG_real;     // fused: rho(k) rides in the same kernel (six virtual slots) and ONE kernel finishes the frame
 	size_t smem;
 };

@@ -16,9 +16,30 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-template <int C, int SPW, bool VARBOX>
-__global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_kernel(const MmaArgs a)
+#ifdef SQT_PHASE_TIMING
+// diagnostic build (make timing; profiles/probes/vec_phase.py): per-warp clocks of the kernel's phases, summed over warps
+// [0] prologue [1] particle loop [2] butterfly + row store [3] fence + group counter [4] group sum (last warp only)
+// [5] histogram flush [6] warps [7] last warps [8] steps [9] max whole-warp cycles
+__device__ unsigned long long g_vec_tim[16];
+extern "C" void sqt_debug_vec_tim(unsigned long long *out16)
 {
+	if (out16) cudaMemcpyFromSymbol(out16, g_vec_tim, sizeof(unsigned long long) * 16);
+	unsigned long long z[16] = {0};
+	cudaMemcpyToSymbol(g_vec_tim, z, sizeof(z));
+}
+#define VT(i) do { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_vec_tim[i], (unsigned long long)(t_ - vt_)); vt_ = t_; } while (0)
+#else
+#define VT(i) do {} while (0)
+#endif
+
+template <int C, int SPW, bool VARBOX, int MINB>
+__global__ void __launch_bounds__(128, MINB) self_ring_vec_kernel(const MmaArgs a)
+{
+#ifdef SQT_PHASE_TIMING
+	long long vt_ = clock64();
+	const long long vt0_ = vt_;
+	int vsteps_ = 0;
+#endif
 	extern __shared__ long long s_mem[];
 	const int wpb = blockDim.x >> 5;
 	const int SB = wpb * SPW;
@@ -58,51 +79,88 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 	const double *cx = a.cur, *cy = cx + a.cur_pitch, *cz = cy + a.cur_pitch;
 	const long long RP = a.RP;
 	const int nws = (a.total_warps - wsg + a.NWSG - 1) / a.NWSG;
+	// Tile hand-out in two halves so that the counter's round trip to L2 is never waited for: the request for the tile
+	// after the current one is issued when a tile starts and only resolved when that tile's last step is prepared.
 	int jgrab = 0;
-	auto grab = [&]() -> int {
-		int t;
-		if (a.dynamic) {
-			t = 0;
-			if (lane == 0) t = atomicAdd(&a.tile_ctr[wsg], 1);
-		} else {
-			t = kq + jgrab * nws;
-			++jgrab;
-		}
+	auto grab_issue = [&]() -> int {
+		int t = 0;
+		if (a.dynamic) { if (lane == 0) t = atomicAdd(&a.tile_ctr[wsg], 1); }
+		else { t = kq + jgrab * nws; ++jgrab; }
+		return t;
+	};
+	auto grab_finish = [&](int t) -> int {
 		t = __reduce_max_sync(0xffffffffu, t);
 		return t < a.ntiles ? t : -1;
 	};
 
+	VT(0);
 	if (live_m) {
-		for (int tile = grab(); tile >= 0; tile = grab()) {
-			const int tbase = tile * a.tile;
-			int tlen = a.n_local - tbase;
-			tlen = tlen < a.tile ? tlen : a.tile;
-			for (int i0 = 0; i0 < tlen; i0 += 32) {
-				const bool valid = i0 + lane < tlen;
-				const long long n = tbase + (valid ? i0 + lane : tlen - 1);
-				const double rx = __ldg(cx + n), ry = __ldg(cy + n), rz = __ldg(cz + n);
-				if (virt) {
+		// The loop runs over 32-particle steps.  ncu (profiles/r2_ncu_full_vec_c1.txt) showed the first version waiting on its
+		// own loads (long_scoreboard 3.2 warps per issue, FP64 pipe 34 % busy at 4 warps per scheduler): every step's current
+		// positions and origin rows are therefore fetched one step ahead, while the previous step's chains run.
+		int pend = grab_issue();
+		int tile = grab_finish(pend);
+		int i0 = 0, tbase = 0, tlen = 0;
+		bool have = tile >= 0;
+		if (have) { tbase = tile * a.tile; tlen = a.n_local - tbase; tlen = tlen < a.tile ? tlen : a.tile; pend = grab_issue(); }
+		bool pvalid = false;
+		long long pn = 0;
+		double prx = 0.0, pry = 0.0, prz = 0.0, pox[SPW], poy[SPW], poz[SPW];
 #pragma unroll
-					for (int s = 0; s < SPW; ++s) {
-						if (!((live_m >> s) & 1)) continue;
-						const int ax = (v0 + s) >> 1, im = (v0 + s) & 1;
-						const double xa = ax == 0 ? rx : (ax == 1 ? ry : rz);
-						const double u = xa * invL;
-						const double c = mma_cos2pi(u);
-						double x = im ? mma_cos2pi(u - 0.25) : c;  // sin(k x) / cos(k x): the seeds of lmp2sqt.c:1180-1186
-						double pv = im ? 0.0 : 1.0;                 // x_0 = sin 0 / cos 0
-						if (!valid) { x = 0.0; pv = 0.0; }
-						const double t = c + c;
+		for (int s = 0; s < SPW; ++s) { pox[s] = 0.0; poy[s] = 0.0; poz[s] = 0.0; }
+		auto load_step = [&](int tb, int tl, int i) {
+			pvalid = i + lane < tl;
+			pn = tb + (pvalid ? i + lane : tl - 1);
+			prx = __ldg(cx + pn); pry = __ldg(cy + pn); prz = __ldg(cz + pn);
+			if (!virt) {
+				const double *rrow = a.ring + (long long)slot0 * 3 * RP + pn; // [slot][axis][particle]
 #pragma unroll
-						for (int m = 0; m < C; ++m) {
-							acc[s][m] += x;
-							const double nx = fma(t, x, -pv);
-							pv = x; x = nx;
-						}
-						if (!im && valid) msd[s] += xa;            // the cos slots also carry sum_n r_a (for MSDCM)
+				for (int s = 0; s < SPW; ++s)
+					if (((live_m >> s) & 1) && !((cap_m >> s) & 1)) {
+						const double *rs = rrow + (long long)s * 3 * RP;
+						pox[s] = __ldg(rs); poy[s] = __ldg(rs + RP); poz[s] = __ldg(rs + 2 * RP);
 					}
-					continue;
+			}
+		};
+		if (have) load_step(tbase, tlen, 0);
+		while (have) {
+			const bool valid = pvalid;
+			const long long n = pn;
+			const double rx = prx, ry = pry, rz = prz;
+			double cox[SPW], coy[SPW], coz[SPW];
+#pragma unroll
+			for (int s = 0; s < SPW; ++s) { cox[s] = pox[s]; coy[s] = poy[s]; coz[s] = poz[s]; }
+			// the step after this one: its loads go out now
+			int ni0 = i0 + 32, ntbase = tbase, ntlen = tlen;
+			bool nhave = true;
+			if (ni0 >= tlen) {
+				const int nt = grab_finish(pend);
+				if (nt < 0) nhave = false;
+				else { ntbase = nt * a.tile; ntlen = a.n_local - ntbase; ntlen = ntlen < a.tile ? ntlen : a.tile; ni0 = 0; pend = grab_issue(); }
+			}
+			if (nhave) load_step(ntbase, ntlen, ni0);
+
+			if (virt) {
+#pragma unroll
+				for (int s = 0; s < SPW; ++s) {
+					if (!((live_m >> s) & 1)) continue;
+					const int ax = (v0 + s) >> 1, im = (v0 + s) & 1;
+					const double xa = ax == 0 ? rx : (ax == 1 ? ry : rz);
+					const double u = xa * invL;
+					const double c = mma_cos2pi(u);
+					double x = im ? mma_cos2pi(u - 0.25) : c;  // sin(k x) / cos(k x): the seeds of lmp2sqt.c:1180-1186
+					double pv = im ? 0.0 : 1.0;                 // x_0 = sin 0 / cos 0
+					if (!valid) { x = 0.0; pv = 0.0; }
+					const double t = c + c;
+#pragma unroll
+					for (int m = 0; m < C; ++m) {
+						acc[s][m] += x;
+						const double nx = fma(t, x, -pv);
+						pv = x; x = nx;
+					}
+					if (!im && valid) msd[s] += xa;            // the cos slots also carry sum_n r_a (for MSDCM)
 				}
+			} else {
 				double *rrow = a.ring + (long long)slot0 * 3 * RP + n; // [slot][axis][particle]
 #pragma unroll
 				for (int s = 0; s < SPW; ++s) {
@@ -113,7 +171,7 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 					if (capture) {
 						ox = rx; oy = ry; oz = rz;
 						if (valid) { rs[0] = rx; rs[RP] = ry; rs[2 * RP] = rz; } // SetWaitedTimeCorr, lmp2sqt.c:1279-1282
-					} else { ox = __ldg(rs); oy = __ldg(rs + RP); oz = __ldg(rs + 2 * RP); }
+					} else { ox = cox[s]; oy = coy[s]; oz = coz[s]; }
 					const double dx = rx - ox, dy = ry - oy, dz = rz - oz; // lmp2sqt.c:1407-1409
 					// un-fused like the reference's x86-64 build so that dr2, hence the bin, is bit-identical
 					const double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -144,8 +202,13 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 					}
 				}
 			}
+			i0 = ni0; tbase = ntbase; tlen = ntlen; have = nhave;
+#ifdef SQT_PHASE_TIMING
+			++vsteps_;
+#endif
 		}
 	}
+	VT(1);
 
 	// lane sums -> warp sums by a fixed butterfly; partial rows [slot group][k-th warp][slot][C + 2]
 	if (kq < a.KW) {
@@ -161,6 +224,7 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 			}
 		}
 	}
+	VT(2);
 	if (a.done_ctr) {
 		// fused small-shape path: whichever warp of this slot group posts its rows last also sums the group's rows -- in row
 		// order, so the result does not depend on which warp that is -- and writes them to their final place: F_s / MSD / MQD
@@ -169,6 +233,7 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 		int last = 0;
 		if (lane == 0) last = atomicAdd(&a.done_ctr[wsg], 1) == nws - 1;
 		last = __shfl_sync(0xffffffffu, last, 0);
+		VT(3);
 		if (last) {
 			__threadfence();
 			const long long stride = (long long)SPW * (C + 2);
@@ -193,6 +258,10 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 					}
 				}
 			}
+#ifdef SQT_PHASE_TIMING
+			VT(4);
+			if (lane == 0) atomicAdd(&g_vec_tim[7], 1ull);
+#endif
 		}
 	}
 	__syncthreads();
@@ -205,6 +274,14 @@ __global__ void __launch_bounds__(128, (C * SPW > 20) ? 4 : 5) self_ring_vec_ker
 			atomicAdd(&a.hist_cur[sl * nCS + e % nCS], cntv);
 		}
 	}
+#ifdef SQT_PHASE_TIMING
+	VT(5);
+	if (lane == 0) {
+		atomicAdd(&g_vec_tim[6], 1ull);
+		atomicAdd(&g_vec_tim[8], (unsigned long long)vsteps_);
+		atomicMax(&g_vec_tim[9], (unsigned long long)(clock64() - vt0_));
+	}
+#endif
 }
 
 // one block per origin slot: fixed-order sum of the per-warp rows, scatter to the TBuf layout (F_s_qq2 / rrMSD / rrMQD /
@@ -352,14 +429,20 @@ int sqt_launch_vec_finish(const VecFinishArgs &a, cudaStream_t st)
 }
 
 typedef void (*vec_fn)(const MmaArgs);
-static vec_fn vec_variant(int C, int SPW, int varbox)
+// MINB = resident blocks per SM the register allocation is bounded for (launch bounds)
+static vec_fn vec_variant(int C, int SPW, int varbox, int minb)
 {
-#define VV(C_, SPW_) if (C == C_ && SPW == SPW_) return varbox ? (vec_fn)self_ring_vec_kernel<C_, SPW_, true> : (vec_fn)self_ring_vec_kernel<C_, SPW_, false>;
-	VV(4, 2) VV(8, 2) VV(12, 2)
-	VV(16, 1) VV(20, 1) VV(24, 1) VV(28, 1) VV(32, 1)
+#define VV(C_, SPW_, M_) if (C == C_ && SPW == SPW_ && minb == M_) return varbox ? (vec_fn)self_ring_vec_kernel<C_, SPW_, true, M_> : (vec_fn)self_ring_vec_kernel<C_, SPW_, false, M_>;
+	VV(4, 2, 5) VV(8, 2, 5) VV(12, 2, 4) VV(12, 2, 5)
+	VV(4, 1, 8) VV(8, 1, 8) VV(12, 1, 6) VV(12, 1, 8)
+	VV(16, 1, 5) VV(20, 1, 5) VV(24, 1, 4) VV(28, 1, 4) VV(32, 1, 4) VV(32, 1, 3)
 #undef VV
 	return nullptr;
 }
+// measured on B200 (profiles/README.md, small shapes): C = 32 needs 168 registers to keep its 32 running sums and the
+// prefetched step out of local memory (3 blocks per SM beat 4 spilling ones, 30.9 vs 37.7 us at config 1); C <= 12 runs best
+// with ONE slot per warp at 80 registers, 6 blocks per SM (91 vs 98 us at config 2; 8 blocks at 64 registers spill: 103 us)
+static int vec_default_minb(int C, int SPW) { return SPW == 1 && C <= 12 ? (C <= 8 ? 8 : 6) : (C * SPW > 28 ? 3 : (C * SPW > 20 ? 4 : 5)); }
 
 static int vec_env_int(const char *name, int dflt)
 {
@@ -373,20 +456,23 @@ int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, int fuse, Ve
 	const int want = vec_env_int("SQT_VEC", -1);
 	if (want == 0 || B < 1 || nCS < 1 || nChain < 1 || nChain > 32) return 0;
 	const int C = (nChain + 3) / 4 * 4;
-	const int SPW = C <= 12 ? 2 : 1; // 2 C SPW registers of running sums per lane
+	int SPW = 1;               // origin slots per warp (2 C SPW registers of running sums per lane)
+	if (C <= 12 && vec_env_int("SQT_VEC_SPW", 0) == 2) SPW = 2;
+	int minb = vec_env_int("SQT_VEC_MINB", vec_default_minb(C, SPW));
+	if (!vec_variant(C, SPW, 0, minb)) minb = vec_default_minb(C, SPW);
 	const int W = 4;
 	const size_t sm = sizeof(long long) * (nCS + 2) + sizeof(int) * (size_t)nCS * W * SPW;
 	for (int vb = 0; vb < 2; ++vb) {
-		cudaError_t e = cudaFuncSetAttribute((const void *)vec_variant(C, SPW, vb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+		cudaError_t e = cudaFuncSetAttribute((const void *)vec_variant(C, SPW, vb, minb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 		if (e != cudaSuccess) return (int)e;
 	}
 	int occ = 0;
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)vec_variant(C, SPW, 0), W * 32, sm);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)vec_variant(C, SPW, 0, minb), W * 32, sm);
 	if (e != cudaSuccess) return (int)e;
 	if (occ < 1) return 0;
 	cudaFuncAttributes fa;
-	cudaFuncGetAttributes(&fa, (const void *)vec_variant(C, SPW, 0));
-	vc->C = C; vc->SPW = SPW; vc->WPB = W; vc->occ = occ; vc->regs = fa.numRegs; vc->smem = sm;
+	cudaFuncGetAttributes(&fa, (const void *)vec_variant(C, SPW, 0, minb));
+	vc->C = C; vc->SPW = SPW; vc->minb = minb; vc->WPB = W; vc->occ = occ; vc->regs = fa.numRegs; vc->smem = sm;
 	vc->NWSG_real = (B + SPW - 1) / SPW;
 	vc->fused = fuse && C >= nCS && vec_env_int("SQT_FUSE", 1) != 0; // the virtual rho slots need all nCSpatial chains
 	vc->NWSG = vc->NWSG_real + (vc->fused ? (SQT_NVIRT + SPW - 1) / SPW : 0);
@@ -395,7 +481,7 @@ int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, int fuse, Ve
 	long long ts = n_local / (4 * warps_per_group); // about 4 tiles per warp, a multiple of 32, 32 .. 256 particles
 	ts = (ts / 32) * 32;
 	if (ts < 32) ts = 32;
-	if (ts > 256) ts = 256;
+	if (ts > 128) ts = 128;    // (the hand-out of the next tile is requested a tile ahead, so short tiles cost nothing)
 	const int fT = vec_env_int("SQT_TILE", 0);
 	if (fT > 0) ts = ((fT + 31) / 32) * 32;
 	vc->tile = (int)ts;
@@ -413,7 +499,7 @@ int sqt_pick_vec(int nCS, int nChain, int B, int n_local, int n_sm, int fuse, Ve
 
 int sqt_launch_vec(const VecChoice &vc, const MmaArgs &a, cudaStream_t st)
 {
-	vec_fn fn = vec_variant(vc.C, vc.SPW, a.varbox);
+	vec_fn fn = vec_variant(vc.C, vc.SPW, a.varbox, vc.minb);
 	if (!fn) return -1;
 	fn<<<vc.blocks, vc.WPB * 32, vc.smem, st>>>(a);
 	return (int)cudaGetLastError();
