@@ -23,12 +23,20 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <getopt.h>
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
+
+static double now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static void die_engine(sqt_multi *m, const char *what, int rc)
 {
@@ -192,6 +200,7 @@ int main(int argc, char **argv)
 	bool types_set = n_types <= 1;
 
 	int full_n_snaps_index = 0, progress = -1;
+	const double t_loop0 = now_s();
 	double kVal = deck.kVal;
 	for (int a = optind; a < argc; a++) {
 		if (!files_on[a]) continue;
@@ -255,12 +264,14 @@ int main(int argc, char **argv)
 	}
 	rc = sqt_multi_finish(h, &res);
 	if (rc < 0) die_engine(h, "sqt_finish", rc);
+	const double t_loop = now_s() - t_loop0; /* second pass over the files: read, copy, compute, until the last result is back */
 	if (rc == 1) { /* lmp2sqt.c:327-333 */
 		fprintf(stderr, "limit corr  = %d, countCorrAv = %d\n", limitCorrAv, res.countCorrAv);
 		if (sqt_host_print_process_x(NULL, &res, &deck, &fl, NULL) || sqt_host_print_types(NULL, &res, &deck, &fl, NULL)) { perror("PrintProcess"); exit(1); }
 	}
-	fprintf(stderr, "engine: %d GPU%s; %s; %lld kernel launches\n", sqt_multi_n_gpus(h), sqt_multi_n_gpus(h) > 1 ? "s, particle-sharded" : "",
-	        sqt_kernel_config(sqt_multi_handle(h, 0)), sqt_multi_kernel_launches(h));
+	fprintf(stderr, "engine: %d GPU%s; %s; %lld kernel launches; frame loop %.3f s = %.1f frames/s\n", sqt_multi_n_gpus(h),
+	        sqt_multi_n_gpus(h) > 1 ? "s, particle-sharded" : "", sqt_kernel_config(sqt_multi_handle(h, 0)), sqt_multi_kernel_launches(h),
+	        t_loop, full_n_snaps_index / (t_loop > 0 ? t_loop : 1));
 	sqt_results_free(&res);
 	sqt_multi_destroy(h);
 	for (int a = optind; a < argc; a++) sqt_reader_close(readers[a]);

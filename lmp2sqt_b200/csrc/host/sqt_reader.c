@@ -572,9 +572,22 @@ int sqt_reader_read_atoms_vm(sqt_reader *r, const sqt_frame_header *hd, double *
 	if (mux && (r->raw != 0 || (hd->style != 2 && hd->style != 3))) { r->pos = r->size; return 0; }
 	const int nv = (vx ? 3 : 0) + (mux ? 3 : 0);
 	if (r->raw == 2) return lb_walk_atoms(r, hd, x, y, z, vx, vy, vz);
-	if (r->raw) { /* already SoA: three straight copies into the staging buffer */
+	if (r->raw) { /* already SoA: straight copies into the staging buffer, in 1 MiB pieces shared by the reader's threads (one
+	               * thread moves about 6 GB/s out of the page cache: 4 ms per million atoms, which set the pace at 8 GPUs) */
 		const char *src = r->base + r->pos;
-		memcpy(x, src, (size_t)n * 8); memcpy(y, src + (size_t)n * 8, (size_t)n * 8); memcpy(z, src + (size_t)n * 16, (size_t)n * 8);
+		double *dst[3] = { x, y, z };
+		const size_t bytes = (size_t)n * 8, piece = (size_t)1 << 20, np = (bytes + piece - 1) / piece;
+		int T = r->n_threads;
+		if ((size_t)T > 3 * np) T = (int)(3 * np);
+		if (T < 1 || n < 262144) T = 1;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(T) schedule(static) if (T > 1)
+#endif
+		for (long long k = 0; k < (long long)(3 * np); k++) {
+			const int a = (int)(k / (long long)np);
+			const size_t off = (size_t)(k % (long long)np) * piece, len = off + piece <= bytes ? piece : bytes - off;
+			memcpy((char *)dst[a] + off, src + (size_t)a * bytes + off, len);
+		}
 		r->pos += (size_t)n * 24;
 		return 1;
 	}

@@ -94,6 +94,7 @@ struct sqt_handle {
 	cudaStream_t s_main, s_copy, s_coll, s_aux;
 	cudaEvent_t ev_red, ev_coll, ev_rho, ev_rhoc, ev_prod, ev_t0, ev_t1;
 	bool coll_pending, rhoc_pending;
+	bool rho_reader;          // the caller reads per-frame results (sqt_get_rho / _kvel / _kmu): see run_frame, stage A
 	SqtComm *comm;
 	int rank, nranks;
 	long long launches;
@@ -241,7 +242,7 @@ extern "C" int sqt_create(const sqt_params *p, sqt_handle **out)
 	for (int t = 0; t < SQT_MAX_TYPES; ++t) { h->type_start[t] = h->type_count[t] = 0; h->type_total[t] = 0; }
 	h->latched = false; h->latched_count = 0; h->latched_limit = 0;
 	h->comm = nullptr; h->rank = 0; h->nranks = 1; h->launches = 0; h->prof = false; h->prof_used = 0;
-	h->coll_pending = h->rhoc_pending = false;
+	h->coll_pending = h->rhoc_pending = false; h->rho_reader = false;
 	h->s_main = h->s_copy = h->s_coll = h->s_aux = nullptr;
 	h->ev_copy[0] = h->ev_copy[1] = h->ev_ring[0] = h->ev_ring[1] = nullptr;
 	h->ev_red = h->ev_coll = h->ev_rho = h->ev_rhoc = h->ev_prod = h->ev_t0 = h->ev_t1 = nullptr;
@@ -829,6 +830,13 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 			if (h->flag_s) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
 			rc = stage_collective(h, p, n_total, split);
 			if (rc) return rc;
+			// A caller that waits for every frame's rho(k) must not find its allreduce parked behind the self-term kernel: that
+			// kernel is persistent and fills every SM, so an NCCL kernel that becomes ready a moment later gets no SM until it
+			// ends (measured at 8 GPUs: sqt_get_rho returned 17 ms late and the next frame's H2D copy lost its overlap, e2e
+			// 18.8 vs 17.1 ms per frame).  Once the caller has shown that it reads per-frame results, the self-term kernel is
+			// held back until the frame's collective stage is done (an allreduce latency per frame); free-running callers
+			// keep the fully asynchronous order.
+			if (split && h->rho_reader) CU(cudaStreamWaitEvent(h->s_main, h->ev_rhoc, 0));
 		}
 	}
 
@@ -1167,6 +1175,7 @@ extern "C" const char *sqt_kernel_config(const sqt_handle *h) { return h ? h->cf
 static int read_rho_block(sqt_handle *h, double *out, int offset)
 {
 	CU(cudaSetDevice(h->device));
+	h->rho_reader = true;
 	if (h->rhoc_pending) CU(cudaStreamWaitEvent(h->s_aux, h->ev_rhoc, 0));
 	CU(cudaMemcpyAsync(out, h->d_rho_cur + offset, sizeof(double) * 6 * h->S, cudaMemcpyDeviceToHost, h->s_aux));
 	CU(cudaStreamSynchronize(h->s_aux));

@@ -3,7 +3,8 @@
 kernel-only figures separately"): 1 000 188 atoms, nCSpatial 86, ring 150/150, frames from a raw binary frame file
 (SQTRAW01, the high-rate frame source of section 8f.1) written by the on-device source, through
 `lmp2sqt_b200.out -F -t [-g N]` -- one reader thread, one pinned frame, N chunk copies.
-usage: python profiles/cli_ingest_c3.py [n_frames=240] [gpus=1,8]   -> one JSON line"""
+usage: python profiles/cli_ingest_c3.py [n_frames=240] [gpus=1,8] [nCSpatial=86 nCTime=150 nCBuffer=150]   -> one JSON line
+(a small deck, e.g. `240 1 10 10 10`, makes the GPU work negligible: what is left is the reader's own pace)"""
 import json, os, struct, subprocess, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,6 +15,8 @@ from lmp2sqt_b200 import SynthSource, _lib, synth
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 240
 gpus = [int(g) for g in (sys.argv[2] if len(sys.argv) > 2 else "1").split(",")]
 n_cells, S, T, B = 63, 86, 150, 150
+if len(sys.argv) > 5:
+    S, T, B = int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
 n = 4 * n_cells ** 3
 base = "/dev/shm" if os.path.isdir("/dev/shm") and os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize > 2 * frames * n * 24 else None
 with tempfile.TemporaryDirectory(dir=base) as td:
@@ -31,6 +34,7 @@ with tempfile.TemporaryDirectory(dir=base) as td:
             f.write(buf.tobytes())
     src.close()
     res = {"atoms": n, "frames": frames, "nCSpatial": S, "ring": "%d/%d" % (T, B), "file_GB": os.path.getsize(dump) / 1e9,
+           "reader_threads": os.environ.get("SQT_READER_THREADS", "auto"),
            "file_written_s": time.time() - t0, "tmp": td.split("/")[1], "runs": {}}
     ref = None
     for g in gpus:
@@ -44,6 +48,9 @@ with tempfile.TemporaryDirectory(dir=base) as td:
         if ref is None:
             ref = out
         same = all(np.allclose(out[k], ref[k], rtol=1e-9, atol=1e-12) for k in ("full-density", "self-density", "self-vanHove"))
-        res["runs"]["g%d" % g] = {"wall_s": w, "frames_per_s": frames / w, "particle_k_frame_per_s": n * 3 * S * frames / w,
-                                  "same_output_as_first_run": bool(same), "engine": r.stderr.strip().split("\n")[-1][:160]}
+        last = r.stderr.strip().split("\n")[-1]
+        loop_s = float(last.split("frame loop ")[1].split(" s")[0])      # the CLI's own clock around the frame loop (second pass)
+        res["runs"]["g%d" % g] = {"wall_s": w, "startup_s": w - loop_s, "frame_loop_s": loop_s, "frames_per_s": frames / loop_s,
+                                  "ms_per_frame": 1e3 * loop_s / frames, "particle_k_frame_per_s": n * 3 * S * frames / loop_s,
+                                  "same_output_as_first_run": bool(same), "engine": last[:120]}
     print(json.dumps(res))
