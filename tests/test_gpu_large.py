@@ -109,3 +109,43 @@ def test_million_atoms_tensor_core_equals_recurrence_kernel(monkeypatch):
         ref = np.abs(b[k])
         tol = 1e-9 * np.maximum(ref, 1e-3 * ref[..., :1] if ref.ndim == 2 else 0.0) + 1e-300
         assert (np.abs(a[k] - b[k]) <= tol).all(), (k, float(np.max(np.abs(a[k] - b[k]) / tol)) * 1e-9)
+
+
+@pytest.mark.parametrize("S,n_atoms,want", [(128, 8500, "self_ring_mma_kernel<NT=2"), (43, 8500, "self_ring_kernel<C=43"), (30, 16384, "self_ring_vec_kernel<C=32")])
+def test_many_tiles_velocity_magnet_stress_match_oracle(S, n_atoms, want):
+    """-V -M -s at many particle tiles per kernel: the weighted passes of the tensor-core rho(k) kernel (static tiles over
+    hundreds of blocks), the velocity ring, the per-axis pass over both ring layouts and sum v (x) r against the restatement."""
+    from test_gpu_fields import _check_fields
+    T = B = 6
+    n_cells = int(np.ceil((n_atoms / 4) ** (1 / 3)))
+    traj = synth.make_trajectory(n_cells=n_cells, n_atoms=n_atoms, n_frames=16, seed=211 + S, box_jitter=0.003)
+    deck = Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res, eng = run_trajectories([traj], deck, "FtVMs")
+    assert eng.kernel_config.startswith(want), eng.kernel_config
+    got = res.to_dict()
+    _, raw, _ = pyoracle.run_port(traj, S, T, B, limitCorrAv=BIG, flags="FtVMs", finish=False)
+    check_raw_sums(got, raw, n_atoms, label="VMs S%d N%d " % (S, n_atoms))
+    _check_fields(got, raw, "FtVMs", "S%d N%d " % (S, n_atoms))
+    eng.close()
+
+
+@pytest.mark.parametrize("S,n_atoms,want", [(128, 8500, "self_ring_mma_kernel<NT=2"), (10, 32000, "self_ring_vec_kernel<C=12")])
+def test_many_tiles_per_type_partials_match_the_numpy_statement(S, n_atoms, want):
+    """Per-type partials with thousands of atoms per species: species ranges that start in the middle of the dump order,
+    several tiles per species pass; config 4's nCSpatial with its 80:20 mixture and config 2's shape with three species."""
+    import pytypes
+    from test_gpu_types import _check_sum_rules, _check_types
+    T = B = 6
+    n_cells = int(np.ceil((n_atoms / 4) ** (1 / 3)))
+    traj = synth.make_trajectory(n_cells=n_cells, n_atoms=n_atoms, n_frames=16, seed=311 + S)
+    nt = 2 if S == 128 else 3
+    traj.types = (np.where(np.arange(n_atoms) % 5 == 0, 2, 1) if nt == 2 else 1 + (np.arange(n_atoms) * 7919 % 13) % 3).astype(np.int32)
+    deck = Deck(limitCorrAv=BIG, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res, eng = run_trajectories([traj], deck, "Ft", n_types=nt)
+    assert eng.kernel_config.startswith(want), eng.kernel_config
+    got = res.to_dict()
+    _check_types(got, pytypes.run_types([traj], traj.types, S, T, B), "S%d N%d " % (S, n_atoms))
+    _check_sum_rules(got, "S%d N%d " % (S, n_atoms))
+    _, raw, _ = pyoracle.run_port(traj, S, T, B, limitCorrAv=BIG, finish=False)
+    check_raw_sums(got, raw, n_atoms, label="typed totals S%d N%d " % (S, n_atoms))
+    eng.close()
