@@ -3,7 +3,8 @@
 kernel-only figures separately"): 1 000 188 atoms, nCSpatial 86, ring 150/150, frames from a raw binary frame file
 (SQTRAW01, the high-rate frame source of section 8f.1) written by the on-device source, through
 `lmp2sqt_b200.out -F -t [-g N]` -- one reader thread, one pinned frame, N chunk copies.
-usage: python profiles/cli_ingest_c3.py [n_frames=240] [gpus=1,8] [nCSpatial=86 nCTime=150 nCBuffer=150]   -> one JSON line
+usage: python profiles/cli_ingest_c3.py [n_frames=240] [gpus=1,8] [nCSpatial=86 nCTime=150 nCBuffer=150 [n_cells=63]]   -> one JSON line
+(config 4: `170 1,8 128 150 150 100` = 4 000 000 atoms, a 16 GB file)
 (a small deck, e.g. `240 1 10 10 10`, makes the GPU work negligible: what is left is the reader's own pace)"""
 import json, os, struct, subprocess, sys, tempfile, time
 import numpy as np
@@ -17,6 +18,8 @@ gpus = [int(g) for g in (sys.argv[2] if len(sys.argv) > 2 else "1").split(",")]
 n_cells, S, T, B = 63, 86, 150, 150
 if len(sys.argv) > 5:
     S, T, B = int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+if len(sys.argv) > 6:
+    n_cells = int(sys.argv[6])
 n = 4 * n_cells ** 3
 base = "/dev/shm" if os.path.isdir("/dev/shm") and os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize > 2 * frames * n * 24 else None
 with tempfile.TemporaryDirectory(dir=base) as td:
