@@ -103,7 +103,7 @@ typedef struct {
 	 *   avDrTable_a [a][nCSpatial][nCTime] van Hove counts of species a                                   (sum over a = avDrTable)
 	 *   rrMSD_a, rrMQD_a [a][nCTime]       sum over the atoms of species a                                (sum over a = rrMSDAv, rrMQDAv)
 	 *   nPtls_a [a]                        atoms of species a over all shards */
-	int n_types;
+	int n_types;             /* species the arrays below are allocated for (sqt_results_alloc_types); must equal the handle's */
 	long long nPtls_a[8];
 	double *avF_ab, *avF_s_a, *avDrTable_a, *rrMSD_a, *rrMQD_a;
 } sqt_results;

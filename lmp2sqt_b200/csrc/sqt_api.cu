@@ -140,11 +140,16 @@ extern "C" int sqt_results_alloc_types(sqt_results *r, int n_types)
 {
 	if (!r || n_types < 2 || n_types > SQT_MAX_TYPES || r->nCSpatial < 1) return SQT_ERR_ARG;
 	const size_t ST = (size_t)r->nCSpatial * r->nCTime, T = r->nCTime, nt = n_types;
-	if (!(r->avF_ab = (double *)calloc(nt * nt * ST, sizeof(double)))) return SQT_ERR_NOMEM;
-	if (!(r->avF_s_a = (double *)calloc(nt * ST, sizeof(double)))) return SQT_ERR_NOMEM;
-	if (!(r->avDrTable_a = (double *)calloc(nt * ST, sizeof(double)))) return SQT_ERR_NOMEM;
-	if (!(r->rrMSD_a = (double *)calloc(nt * T, sizeof(double)))) return SQT_ERR_NOMEM;
-	if (!(r->rrMQD_a = (double *)calloc(nt * T, sizeof(double)))) return SQT_ERR_NOMEM;
+	r->avF_ab = (double *)calloc(nt * nt * ST, sizeof(double));
+	r->avF_s_a = (double *)calloc(nt * ST, sizeof(double));
+	r->avDrTable_a = (double *)calloc(nt * ST, sizeof(double));
+	r->rrMSD_a = (double *)calloc(nt * T, sizeof(double));
+	r->rrMQD_a = (double *)calloc(nt * T, sizeof(double));
+	if (!r->avF_ab || !r->avF_s_a || !r->avDrTable_a || !r->rrMSD_a || !r->rrMQD_a) {
+		free(r->avF_ab); free(r->avF_s_a); free(r->avDrTable_a); free(r->rrMSD_a); free(r->rrMQD_a);
+		r->avF_ab = r->avF_s_a = r->avDrTable_a = r->rrMSD_a = r->rrMQD_a = nullptr;
+		return SQT_ERR_NOMEM;
+	}
 	r->n_types = n_types;
 	return SQT_OK;
 }
@@ -1115,8 +1120,9 @@ static int copy_results(sqt_handle *h, const double *d_blk, sqt_results *out, in
 			for (int j = 0; j < 9; ++j) out->rrMSR2_VR_Av[9 * t + j] = tmp[(3 + j) * T + t];
 		}
 	}
-	out->n_types = 0;
-	if (h->n_types && out->avF_ab) { // the species' sums, allocated by sqt_results_alloc_types
+	if (h->n_types && out->avF_ab) { // the species' sums, allocated by sqt_results_alloc_types (out->n_types = what was allocated)
+		if (out->n_types != h->n_types)
+			return fail(h, SQT_ERR_ARG, "results struct allocated for %d species, the handle has %d", out->n_types, h->n_types);
 		const size_t nt = h->n_types;
 		const double *tb = d_blk + h->tav_off;
 		CU(cudaMemcpy(out->avF_ab, tb, sizeof(double) * nt * nt * ST, cudaMemcpyDeviceToHost));
@@ -1125,7 +1131,6 @@ static int copy_results(sqt_handle *h, const double *d_blk, sqt_results *out, in
 		CU(cudaMemcpy(out->rrMSD_a, tb + nt * nt * ST + 2 * nt * ST, sizeof(double) * nt * T, cudaMemcpyDeviceToHost));
 		CU(cudaMemcpy(out->rrMQD_a, tb + nt * nt * ST + 2 * nt * ST + nt * T, sizeof(double) * nt * T, cudaMemcpyDeviceToHost));
 		for (size_t t = 0; t < nt; ++t) out->nPtls_a[t] = h->type_total[t];
-		out->n_types = h->n_types;
 	}
 	out->countCorrAv = count;
 	out->limitCorrAv = limit;

@@ -182,7 +182,8 @@ def test_cli_per_type_option(tmp_path):
     t = synth.make_trajectory(n_cells=3, n_frames=40, seed=9)
     t.types = np.where(np.arange(t.n_atoms) % 5 == 0, 2, 1).astype(np.int32)
     outs = {}
-    for kind, extra in (("plain", []), ("typed", ["-T", "2"])):
+    two = torch.cuda.device_count() >= 2      # with a second GPU the typed run is also sharded (`-g 2`): one reader, species per shard
+    for kind, extra in (("plain", []), ("typed", ["-T", "2"] + (["-g", "2"] if two else []))):
         d = tmp_path / kind
         d.mkdir()
         synth.write_deck(str(d / "in.lmp2sqt"), limitCorrAv=14825, nCBuffer=5, nCSpatial=7, nCTime=10)
