@@ -182,7 +182,9 @@ int  sqt_buffer_count(const sqt_handle *h, int nb);       /* TBuf.count, lmp2sqt
 int  sqt_number_call_print(const sqt_handle *h);
 /* rho(k) of the last processed frame, [3][nCSpatial][2] (marker layout lmp2sqt.c:1173-1174), reduced over all shards.
  * Waits only for that frame's rho(k) kernel, its allreduce and the F(q,t) update -- not for the frame's self-term kernel,
- * which keeps running while the caller prepares the next frame. */
+ * which keeps running while the caller prepares the next frame.  The first call also tells a sharded engine that its caller
+ * reads per-frame results: from then on every frame's self-term kernel is enqueued behind the frame's allreduce (which could
+ * otherwise not get an SM beside the persistent kernel and would return only when that kernel ends). */
 int  sqt_get_rho(sqt_handle *h, double *out);
 /* With flag_V: the current density kvel_q1 of the last processed frame, same layout (lmp2sqt.c:1203-1208). */
 int  sqt_get_kvel(sqt_handle *h, double *out);
