@@ -851,6 +851,7 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 	const bool lane_family = h->self_kind == SELF_MMA || h->self_kind == SELF_VEC;
 	const bool classic_launch = h->self_kind == SELF_CLASSIC || !h->rmc.on; // its own slots, or just the six virtual rho(k) slots
 	const int Bc = h->self_kind == SELF_CLASSIC ? B : 0; // slots the classic kernel treats as real
+	const bool late_collective = classic_launch && (!h->rmc.on || h->self_kind == SELF_CLASSIC); // rho(k) comes out of the recurrence kernel's reduce
 	auto launch_self = [&](long long off, int cnt) -> int {
 		int lrc;
 		if (lane_family) {
@@ -939,6 +940,9 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 				rc = sqt_launch_axis_msd(xa, h->s_main);
 				if (rc) return fail(h, SQT_ERR_CUDA, "axis_msd_kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
 				h->launches += 2;
+				// on the path whose collective stage follows the reduce kernels, sum_n v (x) r is formed here: it reads the frame,
+				// so it has to be enqueued before ev_ring releases the frame buffer to the copy of the frame after next
+				if (late_collective) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
 			}
 		}
 		if (ti == n_ranges - 1) CU(cudaEventRecord(h->ev_ring[slot], h->s_main)); // d_cur[slot] may be overwritten by the copy of the frame after next
@@ -948,8 +952,7 @@ static int run_frame(sqt_handle *h, int slot, const double *cur, long long cur_p
 			if (rc) return rc;
 		}
 	}
-	if (classic_launch && (!h->rmc.on || h->self_kind == SELF_CLASSIC)) {
-		if (h->flag_s) { rc = launch_sum_vr(h, cur, cur_pitch); if (rc) return rc; }
+	if (late_collective) {
 		rc = stage_collective(h, p, n_total, split);
 		if (rc) return rc;
 	}
@@ -1090,6 +1093,20 @@ extern "C" int sqt_push_frame_device_ex(sqt_handle *h, const double *d_soa, int 
 }
 
 cudaStream_t sqt_internal_copy_stream(sqt_handle *h) { return h->s_copy; }
+
+// What the next sqt_push_frame will return if it succeeds -- SQT_OK or SQT_FLUSH -- from the host's ring bookkeeping alone
+// (the same integers run_frame / accumulate_completed step through; lmp2sqt.c:1612-1615, 1638-1647, 376-443).  Lets
+// sqt_multi_push_frame answer its caller while the per-GPU workers are still enqueuing the frame.
+int sqt_internal_predict_status(const sqt_handle *h)
+{
+	if (h->nSkip < h->p.nCSkip) return SQT_OK; // the frame will be skipped
+	int c = h->countCorrAv, status = SQT_OK;
+	for (int nb = 0; nb < h->B; ++nb)
+		if (h->count[nb] + 1 == h->T) {
+			if (++c == h->limitCorrAv) { status = SQT_FLUSH; c = 0; }
+		}
+	return status;
+}
 
 extern "C" int sqt_sync(sqt_handle *h)
 {
