@@ -1094,20 +1094,6 @@ extern "C" int sqt_push_frame_device_ex(sqt_handle *h, const double *d_soa, int 
 
 cudaStream_t sqt_internal_copy_stream(sqt_handle *h) { return h->s_copy; }
 
-// What the next sqt_push_frame will return if it succeeds -- SQT_OK or SQT_FLUSH -- from the host's ring bookkeeping alone
-// (the same integers run_frame / accumulate_completed step through; lmp2sqt.c:1612-1615, 1638-1647, 376-443).  Lets
-// sqt_multi_push_frame answer its caller while the per-GPU workers are still enqueuing the frame.
-int sqt_internal_predict_status(const sqt_handle *h)
-{
-	if (h->nSkip < h->p.nCSkip) return SQT_OK; // the frame will be skipped
-	int c = h->countCorrAv, status = SQT_OK;
-	for (int nb = 0; nb < h->B; ++nb)
-		if (h->count[nb] + 1 == h->T) {
-			if (++c == h->limitCorrAv) { status = SQT_FLUSH; c = 0; }
-		}
-	return status;
-}
-
 extern "C" int sqt_sync(sqt_handle *h)
 {
 	if (!h) return SQT_ERR_ARG;

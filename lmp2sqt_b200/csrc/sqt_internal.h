@@ -261,7 +261,6 @@ int sqt_launch_sum_vr(const SumVRArgs &a, cudaStream_t st);     // sum_vr_kernel
 // ---- sqt_api.cu internals used by sqt_multi.cu -------------------------------------------------
 struct sqt_handle;
 cudaStream_t sqt_internal_copy_stream(sqt_handle *h); // the stream the handle's H2D copies are issued on
-int sqt_internal_predict_status(const sqt_handle *h); // SQT_OK / SQT_FLUSH the next push will return (host bookkeeping only)
 
 // ---- sqt_comm.cpp -------------------------------------------------------------------------
 struct SqtComm;

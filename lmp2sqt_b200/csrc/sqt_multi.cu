@@ -29,8 +29,6 @@ struct sqt_multi {
 	std::condition_variable cv_go, cv_done;
 	long long gen;
 	int task, ndone;
-	bool inflight;            // a TASK_PUSH was handed to the workers and has not been joined yet
-	int predicted;            // the status sqt_multi_push_frame returned for it
 	// arguments of the current task
 	unsigned char comm_id[SQT_COMM_ID_BYTES];
 	const double *soa;
@@ -125,8 +123,17 @@ static void worker(sqt_multi *m, int g)
 	}
 }
 
-static int collect(sqt_multi *m)
+// runs `task` on every rank (concurrently when G > 1); returns the first negative rc, else rank 0's
+static int dispatch(sqt_multi *m, int task)
 {
+	if (m->G == 1) {
+		m->rc[0] = run_task(m, 0, task);
+	} else {
+		std::unique_lock<std::mutex> lk(m->mu);
+		m->task = task; m->ndone = 0; ++m->gen;
+		m->cv_go.notify_all();
+		m->cv_done.wait(lk, [&] { return m->ndone == m->G; });
+	}
 	for (int g = 0; g < m->G; ++g)
 		if (m->rc[g] < 0) {
 			const char *e = m->h[g] ? sqt_last_error(m->h[g]) : sqt_last_error(nullptr);
@@ -136,47 +143,9 @@ static int collect(sqt_multi *m)
 	return m->rc[0];
 }
 
-// A push is handed to the workers and NOT waited for (the caller reads its next frame meanwhile); every later call joins it
-// first.  Its status was predicted from the host bookkeeping; a worker that disagrees, or fails, is reported by the join.
-static int join_push(sqt_multi *m)
-{
-	if (!m->inflight) return SQT_OK;
-	{
-		std::unique_lock<std::mutex> lk(m->mu);
-		m->cv_done.wait(lk, [&] { return m->ndone == m->G; });
-	}
-	m->inflight = false;
-	const int rc = collect(m);
-	if (rc < 0) return rc;
-	if (rc != m->predicted) return mfail(m, SQT_ERR_STATE, "internal: frame status %d, predicted %d", rc, m->predicted);
-	if (m->stage_slot_of_push >= 0) m->ev_pending[m->stage_slot_of_push] = true;
-	return SQT_OK;
-}
-
-// runs `task` on every rank (concurrently when G > 1); returns the first negative rc, else rank 0's
-static int dispatch(sqt_multi *m, int task)
-{
-	int rc = join_push(m);
-	if (rc < 0) return rc;
-	if (m->G == 1) {
-		m->rc[0] = run_task(m, 0, task);
-	} else {
-		std::unique_lock<std::mutex> lk(m->mu);
-		m->task = task; m->ndone = 0; ++m->gen;
-		m->cv_go.notify_all();
-		m->cv_done.wait(lk, [&] { return m->ndone == m->G; });
-	}
-	return collect(m);
-}
-
 extern "C" const char *sqt_multi_last_error(const sqt_multi *m) { return m ? m->err : g_multi_err; }
 extern "C" int sqt_multi_n_gpus(const sqt_multi *m) { return m ? m->G : 0; }
-extern "C" sqt_handle *sqt_multi_handle(sqt_multi *m, int rank)
-{
-	if (!m || rank < 0 || rank >= m->G) return nullptr;
-	join_push(m); // the handle's host state is the workers' while a push is in flight
-	return m->h[rank];
-}
+extern "C" sqt_handle *sqt_multi_handle(sqt_multi *m, int rank) { return (m && rank >= 0 && rank < m->G) ? m->h[rank] : nullptr; }
 
 extern "C" int sqt_multi_create(const sqt_params *p, sqt_multi **out)
 {
@@ -192,7 +161,7 @@ extern "C" int sqt_multi_create(const sqt_params *p, sqt_multi **out)
 	m->h.assign(G, nullptr); m->rc.assign(G, 0);
 	m->ev[0].assign(G, nullptr); m->ev[1].assign(G, nullptr);
 	m->ev_pending[0] = m->ev_pending[1] = false;
-	m->gen = 0; m->task = TASK_NONE; m->ndone = 0; m->inflight = false; m->predicted = SQT_OK;
+	m->gen = 0; m->task = TASK_NONE; m->ndone = 0;
 	m->h_stage[0] = m->h_stage[1] = nullptr; m->stage_cap = 0; m->stage_next = 0; m->stage_slot_of_push = -1;
 	m->err[0] = 0;
 	if (G > 1)
@@ -217,7 +186,6 @@ extern "C" int sqt_multi_create(const sqt_params *p, sqt_multi **out)
 extern "C" void sqt_multi_destroy(sqt_multi *m)
 {
 	if (!m) return;
-	join_push(m); // (whatever it reports: the handles go away now)
 	dispatch(m, TASK_DESTROY);
 	if (m->G > 1) {
 		{
@@ -235,8 +203,6 @@ extern "C" void sqt_multi_destroy(sqt_multi *m)
 extern "C" int sqt_multi_set_limit(sqt_multi *m, int limitCorrAv)
 {
 	if (!m) return SQT_ERR_ARG;
-	const int jr = join_push(m);
-	if (jr < 0) return jr;
 	for (auto hh : m->h) sqt_set_limit(hh, limitCorrAv);
 	return SQT_OK;
 }
@@ -256,8 +222,6 @@ extern "C" int sqt_multi_set_types(sqt_multi *m, const int *types, int n_atoms)
 extern "C" int sqt_multi_begin_file(sqt_multi *m)
 {
 	if (!m) return SQT_ERR_ARG;
-	const int jr = join_push(m);
-	if (jr < 0) return jr;
 	for (auto hh : m->h) sqt_begin_file(hh);
 	return SQT_OK;
 }
@@ -276,7 +240,6 @@ static int wait_stage(sqt_multi *m, int s)
 extern "C" double *sqt_multi_stage_acquire(sqt_multi *m, int n_atoms)
 {
 	if (!m || n_atoms < 1) return nullptr;
-	if (join_push(m) < 0) return nullptr; // (the buffer handed out now is not the one the workers may still be reading, but its events are theirs)
 	if (n_atoms > m->stage_cap) {
 		for (int s = 0; s < 2; ++s) {
 			if (wait_stage(m, s)) return nullptr;
@@ -298,25 +261,9 @@ extern "C" double *sqt_multi_stage_acquire(sqt_multi *m, int n_atoms)
 extern "C" int sqt_multi_push_frame(sqt_multi *m, const double *soa, int n_atoms, double xlo, double xhi)
 {
 	if (!m || !soa || n_atoms < m->G) return m ? mfail(m, SQT_ERR_ARG, "push_frame: bad arguments (at least one atom per GPU)") : SQT_ERR_ARG;
-	int rc = join_push(m);
-	if (rc < 0) return rc;
 	m->soa = soa; m->n_atoms = n_atoms; m->xlo = xlo; m->xhi = xhi;
 	m->stage_slot_of_push = soa == m->h_stage[0] ? 0 : (soa == m->h_stage[1] ? 1 : -1);
-	// Frames out of the library's own staging buffers are pushed without waiting for the workers: the caller goes on to read
-	// its next frame while the G copy-and-launch sequences are enqueued.  (Foreign buffers: the caller may reuse them as soon
-	// as this returns, so the push is joined here.)
-	static const bool async_ok = !(getenv("SQT_MULTI_ASYNC") && *getenv("SQT_MULTI_ASYNC") == '0');
-	if (m->G > 1 && m->stage_slot_of_push >= 0 && async_ok) {
-		m->predicted = sqt_internal_predict_status(m->h[0]);
-		{
-			std::lock_guard<std::mutex> lk(m->mu);
-			m->task = TASK_PUSH; m->ndone = 0; ++m->gen;
-		}
-		m->cv_go.notify_all();
-		m->inflight = true;
-		return m->predicted;
-	}
-	rc = dispatch(m, TASK_PUSH);
+	const int rc = dispatch(m, TASK_PUSH);
 	if (rc >= 0 && m->stage_slot_of_push >= 0) m->ev_pending[m->stage_slot_of_push] = true;
 	return rc;
 }
@@ -350,7 +297,6 @@ extern "C" int sqt_multi_finish(sqt_multi *m, sqt_results *out) { return (m && o
 extern "C" long long sqt_multi_kernel_launches(const sqt_multi *m)
 {
 	long long n = 0;
-	if (m && m->inflight) join_push(const_cast<sqt_multi *>(m));
 	if (m) for (auto hh : m->h) n += sqt_kernel_launches(hh);
 	return n;
 }
