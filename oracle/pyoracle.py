@@ -404,7 +404,14 @@ def _ref_worker(job_path: str) -> None:
             log.append(ref.countCorrAv)
     raw = ref.arrays()
     out = {"raw": raw, "times": times, "log": log, "n_print": ref.number_call_print}
-    if job.get("normalise", True) and raw["countCorrAv"] > 0:
+    if job.get("print_files") and raw["countCorrAv"] > 0:
+        # the reference's own PrintProcess (lmp2sqt.c:338-367) in the scratch cwd: every file the flag set produces, with the date
+        # suffix "GOLD" (datetime_data is main's job, :127-132); its C2_* streams are never closed, hence the fflush(NULL)
+        C.memmove(C.addressof((C.c_char * 100).in_dll(ref.L, "datetime_data")), b"GOLD\0", 5)
+        ref.L.PrintProcess(C.byref(ref.cl))
+        C.CDLL(None).fflush(None)
+        out["files"] = {fn: open(fn, "rb").read() for fn in sorted(os.listdir(".")) if fn.endswith(".GOLD") or fn.startswith("output.")}
+    elif job.get("normalise", True) and raw["countCorrAv"] > 0:
         ref.pre_print()
         out["printed"] = ref.arrays()
         out["printed"]["countCorrAv"] = raw["countCorrAv"]
@@ -413,7 +420,7 @@ def _ref_worker(job_path: str) -> None:
 
 
 def run_reference(trajs, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, flags="Ft", threads=1,
-                  limit=10**9, normalise=True) -> dict:
+                  limit=10**9, normalise=True, print_files=False) -> dict:
     """Run the unmodified reference in a fresh process over ``trajs`` (list of Trajectory = input
     files).  ``limit`` is the in-memory limitCorrAv (default: never flush mid-run, so that the raw
     sums of the whole run can be read).  OMP_NUM_THREADS=``threads`` (1 for anything MSD-like: the
@@ -421,7 +428,7 @@ def run_reference(trajs, nCSpatial, nCTime, nCBuffer, nCSkip=0, rVal=0.2, flags=
     if not have_reference():
         raise RuntimeError("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")
     with tempfile.TemporaryDirectory() as td:
-        job = {"cwd": td, "out": os.path.join(td, "out.pkl"), "limit": int(limit), "normalise": normalise,
+        job = {"cwd": td, "out": os.path.join(td, "out.pkl"), "limit": int(limit), "normalise": normalise, "print_files": print_files,
                "params": dict(nCSpatial=nCSpatial, nCTime=nCTime, nCBuffer=nCBuffer, nCSkip=nCSkip, rVal=rVal, flags=flags),
                "files": [(t.positions, t.box, t.velocities if ("V" in flags or "s" in flags) else None,
                           t.dipoles if "M" in flags else None) for t in trajs]}

@@ -550,3 +550,59 @@ def test_mmap_reader_dipole_and_velocity_columns(tmp_path):
     txt[9] = " ".join(txt[9].split()[:5] + ["0.000100", "0.000200", "0.000100"])
     (tmp_path / "tiny").write_text("\n".join(txt))
     assert not read(tmp_path / "tiny", False, True)[0][6:9, 0].any()
+
+
+# ---- the writers against the reference's own PrintProcess run in-process, every flag combination (incl. -V -M, which no dump
+# file can exercise through the reference's reader) ------------------------------------------------------------------------------
+PRINT_FLAGS = ["FtVMs", "FtVM", "ftV", "fM", "ts", "FtMs", "fVM"]
+FROZEN_PRINT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "print_process_flags.pkl")
+
+
+def _print_case(flags):
+    traj = synth.make_trajectory(n_cells=2, n_frames=40, seed=5 + len(flags), box_jitter=0.004)
+    return traj, 5, 8, 4
+
+
+def _check_print_files(flags, ref_files, tmp_path):
+    traj, S, T, B = _print_case(flags)
+    extra = (traj.n_frames - T) // (T // B)
+    printed, raw, log = pyoracle.run_port(traj, S, T, B, limitCorrAv=10**9 - extra, flags=flags)   # same limitCorrAv as the reference run
+    res = _results_from_x(printed["_raw_at_print"], S, T, flags)
+    deck = Deck(limitCorrAv=0, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res.print_process(str(tmp_path), deck, flags, date="GOLD")
+    made = sorted(os.listdir(tmp_path))
+    assert made == sorted(ref_files), (flags, made, sorted(ref_files))          # the same set of files ...
+    for fn in made:
+        a, b = (tmp_path / fn).read_bytes(), ref_files[fn]
+        if fn.startswith("Dt") and "s" not in flags:                            # (msdx msdy msdz: unset memory in the reference without -s)
+            assert dt_rows_without_uninitialised_columns(a.decode()) == dt_rows_without_uninitialised_columns(b.decode()), (flags, fn)
+        elif fn == "output.log":
+            assert a.split()[:4] == b.split()[:4]                               # (the last field is limitCorrAv: 10^9 there, as given here)
+        else:
+            assert a == b, (flags, fn)                                          # ... byte for byte
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("flags", PRINT_FLAGS)
+def test_writers_equal_reference_printprocess_in_process(flags, tmp_path):
+    traj, S, T, B = _print_case(flags)
+    ref = pyoracle.run_reference([traj], S, T, B, flags=flags, print_files=True, limit=10**9)
+    _check_print_files(flags, ref["files"], tmp_path)
+
+
+@pytest.mark.parametrize("flags", PRINT_FLAGS)
+def test_writers_equal_frozen_reference_printprocess_files(flags, tmp_path):
+    import pickle
+    with open(FROZEN_PRINT, "rb") as f:
+        frozen = pickle.load(f)
+    _check_print_files(flags, frozen[flags], tmp_path)
+
+
+if __name__ == "__main__":                                                      # regenerate the frozen files (needs oracle/_ref)
+    import pickle
+    out = {}
+    for fl in PRINT_FLAGS:
+        traj, S, T, B = _print_case(fl)
+        out[fl] = pyoracle.run_reference([traj], S, T, B, flags=fl, print_files=True, limit=10**9)["files"]
+    with open(FROZEN_PRINT, "wb") as f:
+        pickle.dump(out, f)
