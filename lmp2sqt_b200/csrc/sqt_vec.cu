@@ -434,15 +434,23 @@ static vec_fn vec_variant(int C, int SPW, int varbox, int minb)
 {
 #define VV(C_, SPW_, M_) if (C == C_ && SPW == SPW_ && minb == M_) return varbox ? (vec_fn)self_ring_vec_kernel<C_, SPW_, true, M_> : (vec_fn)self_ring_vec_kernel<C_, SPW_, false, M_>;
 	VV(4, 2, 5) VV(8, 2, 5) VV(12, 2, 4) VV(12, 2, 5)
-	VV(4, 1, 8) VV(8, 1, 8) VV(12, 1, 6) VV(12, 1, 8)
+	VV(4, 1, 8) VV(8, 1, 8) VV(12, 1, 6) VV(12, 1, 8) VV(12, 1, 5) VV(12, 1, 4) VV(8, 1, 6)
 	VV(16, 1, 5) VV(20, 1, 5) VV(24, 1, 4) VV(28, 1, 4) VV(32, 1, 4) VV(32, 1, 3)
+	VV(16, 1, 4) VV(20, 1, 4) VV(24, 1, 3) VV(28, 1, 3) VV(32, 1, 2) VV(4, 1, 6)
 #undef VV
 	return nullptr;
 }
 // measured on B200 (profiles/README.md, small shapes): C = 32 needs 168 registers to keep its 32 running sums and the
 // prefetched step out of local memory (3 blocks per SM beat 4 spilling ones, 30.9 vs 37.7 us at config 1); C <= 12 runs best
 // with ONE slot per warp at 80 registers, 6 blocks per SM (91 vs 98 us at config 2; 8 blocks at 64 registers spill: 103 us)
-static int vec_default_minb(int C, int SPW) { return SPW == 1 && C <= 12 ? (C <= 8 ? 8 : 6) : (C * SPW > 28 ? 3 : (C * SPW > 20 ? 4 : 5)); }
+// One slot per warp: the largest block count whose register budget keeps the running sums and the prefetched step out of
+// local memory (cuobjdump -res-usage: no stack) -- spills sit in the chain loop and cost more than the lost warps
+// (config 2, C = 12: 80 registers x 6 blocks with 48 B of stack 90.7 us per kernel, 94 x 5 without 80.3 us).
+static int vec_default_minb(int C, int SPW)
+{
+	if (SPW != 1) return C * SPW > 20 ? 4 : 5;
+	return C <= 4 ? 8 : (C <= 8 ? 6 : (C <= 12 ? 5 : (C <= 20 ? 4 : 3)));
+}
 
 static int vec_env_int(const char *name, int dflt)
 {
