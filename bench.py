@@ -277,6 +277,14 @@ def time_workload(wl, K, W, world, rank, local_rank, dist, n_cells_override=0, w
         rho_host = np.zeros((3, S, 2))
         e2e_ms, done = 0.0, 0
         import ctypes as C
+        for i in range(W):   # warm-up of THIS path (untimed): host frames in, the step's result out, like the timed steps below
+            src.next()
+            src.to_host(hpool[i % hp_n].numpy().reshape(3, n_local))
+            rc = eng.lib.sqt_push_frame(eng.h, C.c_void_p(hpool[i % hp_n].data_ptr()), n_local, n_total, 0.0, float(L))
+            if rc < 0:
+                raise RuntimeError(eng.lib.sqt_last_error(eng.h).decode())
+            eng.lib.sqt_get_rho(eng.h, rho_host.ctypes.data)
+        eng.sync()
         while done < K:
             chunk = min(hp_n, K - done)
             for i in range(chunk):
