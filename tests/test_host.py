@@ -606,3 +606,48 @@ if __name__ == "__main__":                                                      
         out[fl] = pyoracle.run_reference([traj], S, T, B, flags=fl, print_files=True, limit=10**9)["files"]
     with open(FROZEN_PRINT, "wb") as f:
         pickle.dump(out, f)
+
+
+def test_per_type_normalisation_and_types_file(tmp_path):
+    """Host side of the per-type partials (an extension): normalisation identities and the
+    types%03d.info.<date> file, from raw sums of the numpy statement (oracle/pytypes.py) -- no GPU needed."""
+    import pytypes
+    traj = synth.make_trajectory(n_cells=2, n_frames=40, seed=21, box_jitter=0.003)
+    ty = (np.arange(traj.n_atoms) % 3 == 0).astype(np.int32) + 1
+    S, T, B = 5, 8, 4
+    tp = pytypes.run_types([traj], ty, S, T, B)
+    printed, raw, _ = pyoracle.run_port(traj, S, T, B, limitCorrAv=10**8, flags="Ft")
+    rp = printed["_raw_at_print"]
+    res = Results(S, T, 2)
+    for k, v in {"avF_qq2": "avF", "StdDevF_qq2": "StdDevF", "avF_s_qq2": "avF_s", "StdDevF_s_qq2": "StdDevF_s", "avF_d_qq2": "avF_d",
+                 "StdDevF_d_qq2": "StdDevF_d", "avDrTable": "avDrTable", "rrMSDAv": "rrMSDAv", "rrMQDAv": "rrMQDAv", "rrMSDCMAv": "rrMSDCMAv"}.items():
+        res.array(k)[...] = rp[v]
+    for k in ("countCorrAv", "limitCorrAv", "nPtls", "g_Vol", "kVal", "first_Vol", "first_limitCorrAv"):
+        setattr(res.c, k, rp[k])
+    nt = 2
+    for name, shape in (("avF_ab", (nt, nt, S, T)), ("avF_s_a", (nt, S, T)), ("avDrTable_a", (nt, S, T)), ("rrMSD_a", (nt, T)), ("rrMQD_a", (nt, T))):
+        np.ctypeslib.as_array(getattr(res.c, name), shape=shape)[...] = tp[name]
+    for a in range(nt):
+        res.c.nPtls_a[a] = int(tp["nPtls_a"][a])
+    assert tp["countCorrAv"] == rp["countCorrAv"]
+    deck = Deck(limitCorrAv=0, nCBuffer=B, nCSpatial=S, nCTime=T)
+    res.normalise(deck, "Ft")
+    fl = _lib.SqtFlags(1, 1, 1, 0, 0, 0)
+    dk = deck.to_c()
+    assert _lib.host_lib().sqt_host_print_types(str(tmp_path).encode(), C.byref(res.c), C.byref(dk), C.byref(fl), b"GOLD") == 0
+    g = res.to_dict()
+    Na = g["nPtls_a"].astype(float)
+    np.testing.assert_allclose(g["avF_s_a"][:, :, 0], 1.0, rtol=1e-12)                                   # F_s,a(q, 0) = 1
+    np.testing.assert_allclose(g["avF_ab"].sum(axis=(0, 1)), g["avF_qq2"], rtol=1e-10, atol=1e-13)      # sum_ab F_ab = F
+    np.testing.assert_allclose((Na[:, None, None] * g["avF_s_a"]).sum(axis=0), Na.sum() * g["avF_s_qq2"], rtol=1e-10)
+    np.testing.assert_allclose((Na[:, None] * g["rrMSD_a"]).sum(axis=0), Na.sum() * g["rrMSDAv"], rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose((Na[:, None, None] * g["avDrTable_a"]).sum(axis=0)[:, 1:], Na.sum() * g["avDrTable"][:, 1:], rtol=1e-10)
+    txt = (tmp_path / "types000.info.GOLD").read_text()
+    assert txt.startswith("# per-type partials: n_types 2, atoms %d %d," % (Na[0], Na[1]))
+    assert [ln for ln in txt.split("\n") if ln.startswith("#")][1:] == ["# F_ab 1 1", "# F_ab 1 2", "# F_ab 2 1", "# F_ab 2 2", "# F_s_a 1", "# F_s_a 2",
+                                                                     "# self-vanHove_a 1", "# self-vanHove_a 2", "# time, then MSD_a MQD_a per species"]
+    blk = txt.split("# F_ab 1 2\n")[1].split("\n\n")[0].split("\n")
+    assert len(blk) == T and blk[3].split()[1:] == [("%8.4e" % g["avF_ab"][0, 1, nk, 3]).strip() for nk in range(S)]
+    # a second print picks the next index
+    assert _lib.host_lib().sqt_host_print_types(str(tmp_path).encode(), C.byref(res.c), C.byref(dk), C.byref(fl), b"GOLD") == 0
+    assert (tmp_path / "types001.info.GOLD").exists()
