@@ -177,3 +177,36 @@ def test_cli_magnet_needs_the_dipole_dump_style(tmp_path):
     r = subprocess.run([_lib.CLI_BIN, "-F", "-t", "-V", "-M", "-i", "in.lmp2sqt", "all.lammpstrj"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-800:]
     assert glob.glob(str(tmp_path / "C2_v_mu00*.info.*")) and glob.glob(str(tmp_path / "C2_mu_v00*.info.*"))
+
+
+def test_integration_snippet_runs_like_the_cli(tmp_path):
+    """INTEGRATION.md sections 3 / 3b as a program (tests/data/integration_snippet.c, run_all): compiled here, run with every
+    flag on an 11-column dump, it must leave the same files as `lmp2sqt_b200.out -F -t -V -M -s` apart from the deck rewrite."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "lmp2sqt_b200")
+    exe = tmp_path / "snippet.out"
+    env = {k: v for k, v in os.environ.items() if k != "CC"}
+    r = subprocess.run(["gcc", "-std=gnu99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "data", "integration_snippet.c"),
+                        "-L", pkg, "-lsqt_b200", "-lsqt_host", "-lm", "-Wl,-rpath," + pkg, "-o", str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    t = synth.make_trajectory(n_cells=2, n_frames=30, seed=4)
+    outs = {}
+    for kind in ("cli", "snippet"):
+        d = tmp_path / kind
+        d.mkdir()
+        # limitCorrAv as the CLI's count pass would leave it (the snippet, like the patch of INTEGRATION.md, starts after that pass)
+        synth.write_deck(str(d / "in.lmp2sqt"), limitCorrAv=14825 if kind == "cli" else 14825 + (30 - 6) // (6 // 3), nCBuffer=3, nCSpatial=5, nCTime=6)
+        synth.write_text_dump(t, str(d / "all.lammpstrj"), velocities=True, dipoles=True)
+        cmd = [_lib.CLI_BIN, "-F", "-t", "-V", "-M", "-s", "-i", "in.lmp2sqt", "all.lammpstrj"] if kind == "cli" else [str(exe), "in.lmp2sqt", "all.lammpstrj", "1"]
+        r = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs[kind] = {f.split(".info")[0] if ".info." in f else f: (d / f).read_bytes() for f in os.listdir(d) if ".info." in f or f.startswith("output.")}
+    assert sorted(outs["cli"]) == sorted(outs["snippet"]) and len(outs["cli"]) == 14
+    for k in outs["cli"]:
+        if k == "output.binary":
+            a, b = (pyoracle.parse_output_binary(str(tmp_path / kind / k), 5, 6) for kind in ("cli", "snippet"))
+            for key in ("full-density", "self-density", "cross-density", "self-vanHove"):
+                np.testing.assert_allclose(a[key], b[key], rtol=1e-9, atol=1e-12)
+        elif k != "output.log":
+            x, y = (np.array([float(v) for ln in outs[kind][k].decode().split("\n") if not ln.startswith("#") for v in ln.split()]) for kind in ("cli", "snippet"))
+            np.testing.assert_allclose(x, y, rtol=1e-3, atol=1e-3 * max(1e-300, np.abs(y).max()), err_msg=k)
