@@ -17,7 +17,7 @@ def _files(top, exts):
 
 
 def test_product_tree_never_touches_the_oracle():
-    pat = re.compile(r"pyoracle|sqt_oracle|libsqt_oracle|oracle/_ref|liblmp2sqt_ref")
+    pat = re.compile(r"pyoracle|pytypes|sqt_oracle|libsqt_oracle|oracle/_ref|liblmp2sqt_ref")
     bad = [p for top in ("lmp2sqt_b200", "include") for p in _files(top, (".py", ".c", ".cpp", ".cu", ".cuh", ".h", "Makefile"))
            if pat.search(open(p, errors="replace").read())]
     assert not bad, bad
