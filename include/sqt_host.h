@@ -86,6 +86,18 @@ int sqt_reader_skip_atoms(sqt_reader *r, const sqt_frame_header *hd);
  * 1 ok / 0 not available. */
 int sqt_reader_peek_types(sqt_reader *r, const sqt_frame_header *hd, int *types);
 
+/* Frame-parallel read-ahead for small text frames (the shipped decks' dumps: 4 000 / 32 000 atoms): after a count pass over the
+ * file (sqt_reader_skip_atoms on every frame, which indexes the atom blocks) and sqt_reader_rewind, n_threads workers parse
+ * whole frames ahead of the caller, `depth` frames at most, and sqt_prefetch_next hands them out in file order: header and one
+ * SoA block x[n] y[n] z[n] [vx vy vz] [mux muy muz] (valid until the next call).  Same acceptance rules as
+ * sqt_reader_read_atoms_vm; the first frame that fails ends the stream, as does max_frames.  NULL if the reader is not an
+ * indexed text dump. */
+typedef struct sqt_prefetch sqt_prefetch;
+long sqt_reader_indexed_frames(const sqt_reader *r);
+sqt_prefetch *sqt_prefetch_start(sqt_reader *r, int want_v, int want_m, int depth, int n_threads, long max_frames);
+int sqt_prefetch_next(sqt_prefetch *p, sqt_frame_header *hd, const double **soa);
+void sqt_prefetch_stop(sqt_prefetch *p);
+
 /* factorDr[nr], lmp2sqt.c:1987-2009, from what the engine recorded at the first processed frame. */
 void sqt_host_factor_dr(const sqt_results *r, double rVal, double *factorDr);
 /* prePrintProcess: normalises r's arrays IN PLACE (like the reference does with its globals). */

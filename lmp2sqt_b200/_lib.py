@@ -155,6 +155,10 @@ HOST_API = [
     ("sqt_host_normalise_types", None, [C.POINTER(SqtResults), C.POINTER(SqtDeck)]),
     ("sqt_host_print_types", C.c_int, [C.c_char_p, C.POINTER(SqtResults), C.POINTER(SqtDeck), C.POINTER(SqtFlags), C.c_char_p]),
     ("sqt_reader_peek_types", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.c_void_p]),
+    ("sqt_reader_indexed_frames", C.c_long, [C.c_void_p]),
+    ("sqt_prefetch_start", C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long]),
+    ("sqt_prefetch_next", C.c_int, [C.c_void_p, C.POINTER(SqtFrameHeader), C.POINTER(C.c_void_p)]),
+    ("sqt_prefetch_stop", None, [C.c_void_p]),
     ("sqt_analysis_load", C.c_int, [C.POINTER(SqtAnalysis), C.c_char_p, C.c_char_p, C.c_int]),
     ("sqt_analysis_from_results", C.c_int, [C.POINTER(SqtAnalysis), C.POINTER(SqtResults), C.POINTER(SqtDeck), C.c_int]),
     ("sqt_analysis_time", C.c_int, [C.POINTER(SqtAnalysis), C.c_int, C.c_double, C.c_char_p]),

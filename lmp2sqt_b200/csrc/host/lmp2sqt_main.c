@@ -216,11 +216,15 @@ int main(int argc, char **argv)
 			double new_dk = (2. * M_PI / L0) * n_mul;
 			fprintf(stderr, "Update for input dk param: %f -> %f \n", kVal, new_dk);
 			kVal = new_dk;
-		}
-		sqt_reader_rewind(rd);
-		fprintf(stderr, "FULL_SNAPS = %5d\n", full_n_snaps);
-		for (long ns = 0; ns < num_data[a]; ns++) {
-			if (!sqt_reader_next_header(rd, &hd)) break;
+			if (want_v && !want_m && hd.style != 1) {
+				/* the reference correlates whatever malloc left in Atom.vx for such dumps (snapshot.c:426-437) */
+				fprintf(stderr, "-V / -s need dumps written as `id type xu yu zu vx vy vz` (file %s)\n", argv[a]);
+				exit(1);
+			}
+			if (want_m && (want_v ? hd.style != 3 : (hd.style != 2 && hd.style != 3))) {
+				fprintf(stderr, "-M needs dumps written as `id type xu yu zu mux muy muz%s` (file %s)\n", want_v ? " vx vy vz" : "", argv[a]);
+				exit(1);
+			}
 			if (!types_set) { /* species from the first frame that is read: line order is fixed for the whole run */
 				int *types = (int *)malloc(sizeof(int) * (size_t)(hd.n_atoms > 0 ? hd.n_atoms : 1));
 				if (!sqt_reader_peek_types(rd, &hd, types)) { fprintf(stderr, "-T needs a text dump with a `type` column (file %s)\n", argv[a]); exit(1); }
@@ -229,6 +233,23 @@ int main(int argc, char **argv)
 				free(types);
 				types_set = true;
 			}
+		}
+		/* small text frames (the shipped decks: 4 000 / 32 000 atoms) are parsed AHEAD, whole frames by a few threads, and taken
+		 * in file order here; large frames keep the in-frame threads of the reader (sqt_host.h) */
+		sqt_prefetch *pf = NULL;
+		{
+			const char *pe = getenv("SQT_PREFETCH");
+			if (!(pe && *pe == '0') && sqt_reader_is_raw(rd) == 0 && hd.n_atoms > 0 && hd.n_atoms < 262144 &&
+			    sqt_reader_indexed_frames(rd) >= num_data[a] && num_data[a] >= 8) {
+				int thr = pe && atoi(pe) > 0 ? atoi(pe) : 6;
+				pf = sqt_prefetch_start(rd, want_v, want_m, 2 * thr + 2, thr, num_data[a]);
+			}
+		}
+		sqt_reader_rewind(rd);
+		fprintf(stderr, "FULL_SNAPS = %5d\n", full_n_snaps);
+		for (long ns = 0; ns < num_data[a]; ns++) {
+			const double *ahead = NULL;
+			if (pf ? !sqt_prefetch_next(pf, &hd, &ahead) : !sqt_reader_next_header(rd, &hd)) break;
 			double *stage = sqt_multi_stage_acquire(h, hd.n_atoms);
 			if (!stage) die_engine(h, "sqt_stage_acquire", -1);
 			const size_t na = (size_t)hd.n_atoms;
@@ -242,8 +263,9 @@ int main(int argc, char **argv)
 				exit(1);
 			}
 			double *sv = want_v ? stage + 3 * na : NULL, *sm = want_m ? stage + (want_v ? 6 : 3) * na : NULL;
-			if (!sqt_reader_read_atoms_vm(rd, &hd, stage, stage + na, stage + 2 * na, sv, sv ? sv + na : NULL, sv ? sv + 2 * na : NULL,
-			                              sm, sm ? sm + na : NULL, sm ? sm + 2 * na : NULL)) break;
+			if (pf) memcpy(stage, ahead, sizeof(double) * na * (size_t)(3 + (want_v ? 3 : 0) + (want_m ? 3 : 0)));
+			else if (!sqt_reader_read_atoms_vm(rd, &hd, stage, stage + na, stage + 2 * na, sv, sv ? sv + na : NULL, sv ? sv + 2 * na : NULL,
+			                                   sm, sm ? sm + na : NULL, sm ? sm + 2 * na : NULL)) break;
 			rc = sqt_multi_push_frame(h, stage, hd.n_atoms, hd.xlo, hd.xhi); /* EvalSpacetimeCorr, :300 */
 			if (rc < 0) die_engine(h, "sqt_push_frame", rc);
 			if (rc == SQT_FLUSH) { /* PrintProcess from AccumSpacetimeCorr, :438-440 */
@@ -260,6 +282,7 @@ int main(int argc, char **argv)
 				fflush(stderr);
 			}
 		}
+		sqt_prefetch_stop(pf);
 		fprintf(stderr, "\nEnd : file : %s\n", argv[a]);
 	}
 	rc = sqt_multi_finish(h, &res);

@@ -683,3 +683,134 @@ int sqt_raw_append_frame(const char *path, int create, long long timestep, long 
 	fclose(fp);
 	return ok ? 0 : -1;
 }
+
+/* ---- frame-parallel read-ahead for SMALL text frames -------------------------------------------------------------------
+ * The shipped decks' dumps (4 000 / 32 000 atoms per frame) are parsed in about 0.15 / 1 ms per frame by one thread, ten
+ * times what the GPU needs for such a frame, and too short for the per-frame fork of sqt_reader_read_atoms to pay (waking
+ * sleeping workers costs more than the parse).  Here whole frames are the unit instead: after the count pass has indexed the
+ * atom blocks, a few threads parse frames AHEAD of the consumer, each frame by one thread into its own slot of a small ring,
+ * and the caller takes them in file order.  No wake-up per frame: the workers only wait when the ring is full.
+ * Semantics are the sequential reader's: frames come in file order; the first frame that fails to parse ends the stream
+ * (lmp2sqt.c:296-297 stops the file there), as does `max_frames`. */
+#include <pthread.h>
+
+struct pf_slot {
+	int state;                 /* 0 empty, 1 being filled, 2 ready, 3 end of stream */
+	long seq;
+	sqt_frame_header hd;
+	double *buf;               /* ncomp arrays of cap doubles */
+	int cap;
+};
+
+struct sqt_prefetch {
+	sqt_reader *r;
+	int want_v, want_m, ncomp, depth, n_threads;
+	long max_frames, next_seq, take_seq;
+	int stop;
+	struct pf_slot *slot;
+	pthread_t *th;
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+};
+
+long sqt_reader_indexed_frames(const sqt_reader *r) { return (r && r->raw == 0) ? (long)r->n_blk : 0; }
+
+static void *pf_worker(void *arg)
+{
+	sqt_prefetch *p = (sqt_prefetch *)arg;
+	for (;;) {
+		pthread_mutex_lock(&p->mu);
+		const long seq = p->next_seq++;
+		struct pf_slot *s = &p->slot[seq % p->depth];
+		while (!p->stop && !(s->state == 0 && s->seq == seq)) pthread_cond_wait(&p->cv, &p->mu); /* the consumer has released seq - depth */
+		if (p->stop) { pthread_mutex_unlock(&p->mu); return NULL; }
+		s->state = 1;
+		pthread_mutex_unlock(&p->mu);
+
+		int ok = seq < p->max_frames && seq < (long)p->r->n_blk;
+		if (ok) {
+			sqt_reader me = *p->r;             /* private cursor over the shared, read-only mapping and index */
+			me.n_threads = 1;
+			me.pos = seq == 0 ? 0 : p->r->blk[seq - 1].end_pos;
+			me.blk_cursor = (size_t)seq;
+			ok = sqt_reader_next_header(&me, &s->hd) && s->hd.n_atoms > 0;
+			if (ok) {
+				const int n = s->hd.n_atoms;
+				if (n > s->cap) {
+					free(s->buf);
+					s->buf = (double *)malloc(sizeof(double) * (size_t)p->ncomp * (size_t)n);
+					s->cap = s->buf ? n : 0;
+				}
+				ok = s->buf != NULL;
+				if (ok) {
+					double *c = s->buf, *v = p->want_v ? c + 3 * (size_t)n : NULL, *u = p->want_m ? c + (p->want_v ? 6 : 3) * (size_t)n : NULL;
+					ok = sqt_reader_read_atoms_vm(&me, &s->hd, c, c + n, c + 2 * (size_t)n, v, v ? v + n : NULL, v ? v + 2 * (size_t)n : NULL,
+					                              u, u ? u + n : NULL, u ? u + 2 * (size_t)n : NULL);
+				}
+			}
+		}
+		pthread_mutex_lock(&p->mu);
+		s->state = ok ? 2 : 3;
+		pthread_cond_broadcast(&p->cv);
+		const int done = !ok;
+		pthread_mutex_unlock(&p->mu);
+		if (done) return NULL;                 /* later frames are never delivered: nothing more for this worker to do */
+	}
+}
+
+sqt_prefetch *sqt_prefetch_start(sqt_reader *r, int want_v, int want_m, int depth, int n_threads, long max_frames)
+{
+	if (!r || r->raw != 0 || r->n_blk == 0) return NULL;   /* text dumps whose count pass indexed the atom blocks */
+	sqt_prefetch *p = (sqt_prefetch *)calloc(1, sizeof(*p));
+	if (!p) return NULL;
+	p->r = r; p->want_v = want_v != 0; p->want_m = want_m != 0; p->ncomp = 3 + (want_v ? 3 : 0) + (want_m ? 3 : 0);
+	p->n_threads = n_threads < 1 ? 1 : (n_threads > 32 ? 32 : n_threads);
+	p->depth = depth < p->n_threads + 1 ? p->n_threads + 1 : depth;
+	p->max_frames = max_frames;
+	p->slot = (struct pf_slot *)calloc((size_t)p->depth, sizeof(struct pf_slot));
+	p->th = (pthread_t *)calloc((size_t)p->n_threads, sizeof(pthread_t));
+	if (!p->slot || !p->th) { free(p->slot); free(p->th); free(p); return NULL; }
+	for (int i = 0; i < p->depth; i++) p->slot[i].seq = i;
+	pthread_mutex_init(&p->mu, NULL);
+	pthread_cond_init(&p->cv, NULL);
+	for (int i = 0; i < p->n_threads; i++)
+		if (pthread_create(&p->th[i], NULL, pf_worker, p) != 0) { p->n_threads = i; break; }
+	if (p->n_threads == 0) { sqt_prefetch_stop(p); return NULL; }
+	return p;
+}
+
+int sqt_prefetch_next(sqt_prefetch *p, sqt_frame_header *hd, const double **soa)
+{
+	if (!p) return 0;
+	pthread_mutex_lock(&p->mu);
+	if (p->take_seq > 0) { /* release the slot handed out by the previous call */
+		struct pf_slot *prev = &p->slot[(p->take_seq - 1) % p->depth];
+		prev->state = 0;
+		prev->seq = p->take_seq - 1 + p->depth;
+		pthread_cond_broadcast(&p->cv);
+	}
+	struct pf_slot *s = &p->slot[p->take_seq % p->depth];
+	while (!((s->state == 2 || s->state == 3) && s->seq == p->take_seq)) pthread_cond_wait(&p->cv, &p->mu);
+	const int ok = s->state == 2;
+	if (ok) {
+		*hd = s->hd;
+		*soa = s->buf;
+		p->take_seq++;
+	}
+	pthread_mutex_unlock(&p->mu);
+	return ok;
+}
+
+void sqt_prefetch_stop(sqt_prefetch *p)
+{
+	if (!p) return;
+	pthread_mutex_lock(&p->mu);
+	p->stop = 1;
+	pthread_cond_broadcast(&p->cv);
+	pthread_mutex_unlock(&p->mu);
+	for (int i = 0; i < p->n_threads; i++) pthread_join(p->th[i], NULL);
+	for (int i = 0; i < p->depth; i++) free(p->slot[i].buf);
+	pthread_mutex_destroy(&p->mu);
+	pthread_cond_destroy(&p->cv);
+	free(p->slot); free(p->th); free(p);
+}

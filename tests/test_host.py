@@ -651,3 +651,54 @@ def test_per_type_normalisation_and_types_file(tmp_path):
     # a second print picks the next index
     assert _lib.host_lib().sqt_host_print_types(str(tmp_path).encode(), C.byref(res.c), C.byref(dk), C.byref(fl), b"GOLD") == 0
     assert (tmp_path / "types001.info.GOLD").exists()
+
+
+def _prefetch_frames(path, want_v, want_m, depth, threads, max_frames):
+    h = _lib.host_lib()
+    r = h.sqt_reader_open(str(path).encode(), 1)
+    hd = SqtFrameHeader()
+    n_snap = 0
+    while h.sqt_reader_next_header(r, C.byref(hd)) and hd.n_atoms > 0 and h.sqt_reader_skip_atoms(r, C.byref(hd)):
+        n_snap += 1
+    assert h.sqt_reader_indexed_frames(r) == n_snap
+    h.sqt_reader_rewind(r)
+    p = h.sqt_prefetch_start(r, int(want_v), int(want_m), depth, threads, min(max_frames, n_snap))
+    frames = []
+    if p:
+        soa = C.c_void_p()
+        ncomp = 3 + 3 * want_v + 3 * want_m
+        while h.sqt_prefetch_next(p, C.byref(hd), C.byref(soa)):
+            a = np.ctypeslib.as_array(C.cast(soa, C.POINTER(C.c_double)), shape=(ncomp, hd.n_atoms)).copy()
+            frames.append((hd.timestep, hd.n_atoms, (hd.xlo, hd.xhi), a))
+        h.sqt_prefetch_stop(p)
+    h.sqt_reader_close(r)
+    return frames, n_snap
+
+
+@pytest.mark.parametrize("threads,depth", [(1, 2), (3, 4), (4, 9)])
+def test_frame_parallel_read_ahead_equals_the_sequential_reader(tmp_path, threads, depth):
+    """sqt_prefetch_*: whole frames parsed ahead by a few threads, handed out in file order -- the same frames, the same
+    numbers, the same stop at the first bad frame as sqt_reader_read_atoms_vm called frame after frame."""
+    t = synth.make_trajectory(n_cells=3, n_atoms=77, n_frames=23, seed=8)
+    h = _lib.host_lib()
+    for name, kw, want_v, want_m in (("plain", {}, False, False), ("vel", {"velocities": True}, True, False), ("all", {"velocities": True, "dipoles": True}, True, True)):
+        p = tmp_path / (name + ".lammpstrj")
+        synth.write_text_dump(t, str(p), **kw)
+        frames, n_snap = _prefetch_frames(p, want_v, want_m, depth, threads, 10**9)
+        assert n_snap == 23 and len(frames) == 23
+        for f, (ts, n, box, a) in enumerate(frames):
+            assert ts == t.timesteps[f] and n == 77 and box == (0.0, t.box[f, 0, 1])
+            assert np.array_equal(a[:3], t.positions[f].T)
+            if want_v:
+                assert np.array_equal(a[3:6], t.velocities[f].T)
+            if want_m:
+                assert np.array_equal(a[6:9], t.dipoles[f].T)
+        assert len(_prefetch_frames(p, want_v, want_m, depth, threads, 7)[0]) == 7           # max_frames
+    # a frame that fails in the parse pass (a short line in frame 5, not the last line) ends the stream there
+    txt = (tmp_path / "plain.lammpstrj").read_text().split("\n")
+    per = 9 + 77
+    txt[5 * per + 9 + 3] = "4 1 0.5"
+    (tmp_path / "bad.lammpstrj").write_text("\n".join(txt))
+    frames, n_snap = _prefetch_frames(tmp_path / "bad.lammpstrj", False, False, depth, threads, 10**9)
+    assert n_snap == 23 and len(frames) == 5
+    assert h.sqt_prefetch_start(None, 0, 0, 4, 2, 10) is None
