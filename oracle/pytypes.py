@@ -20,10 +20,11 @@ from __future__ import annotations
 import numpy as np
 
 
-def run_types(trajs, types, S, T, B, nCSkip=0, rVal=0.2):
-    """``trajs``: list of Trajectory (input files); ``types``: [n] ints 1..n_types.  Returns raw sums (dict)."""
+def run_types(trajs, types, S, T, B, nCSkip=0, rVal=0.2, n_types=None):
+    """``trajs``: list of Trajectory (input files); ``types``: [n] ints 1..n_types (``n_types`` defaults to the largest species
+    present).  Returns raw sums (dict)."""
     types = np.asarray(types)
-    nt = int(types.max())
+    nt = int(n_types) if n_types else int(types.max())
     B = max(1, min(B, T))
     masks = [types == a + 1 for a in range(nt)]
     m = np.arange(1, S + 1)
